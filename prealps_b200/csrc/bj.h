@@ -1,0 +1,81 @@
+// bj.h -- shared layout of the block-Jacobi factor between bj_factor.cu (numeric
+// supernodal Cholesky on the device) and bj_solve.cu (level-scheduled sweeps).
+//
+// Factor layout in HBM (see DESIGN.md "Block-Jacobi"):
+//   every supernode s of the forest (all local diagonal blocks together) has a dense
+//   h x w trapezoid  M_s = [ L_ss^{-1} ; L_bs L_ss^{-1} ]  so that both sweeps are pure
+//   streaming products without any intra-supernode dependency:
+//     forward   [y_s ; u_s] = M_s b_s          (u_s = contribution to the ancestors)
+//     backward  x_s = M_s^T [y_s ; -x_below]
+//   M_s is stored twice, cut into 32-row panels, each panel "k-major":
+//     fwd panel p of s: rows [32p, 32p+32) of M_s,   data[k*32 + r] = M_s(32p + r, k),  k < klen
+//     bwd panel q of s: rows [32q, 32q+32) of M_s^T, data[k*32 + r] = +-M_s(32q + k', 32q + r)
+//   so a warp streams a panel with perfectly coalesced 512-byte loads while the t-wide
+//   input row needed for step k is the same for all lanes (broadcast load).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pcu {
+
+struct FwdPanel {      // one 32-row slice of M_s
+  long long off;       // offset (doubles) into fwd_data
+  long long uoff;      // first row of this supernode's slot in the update buffer U
+  int klen;            // number of k steps (even)
+  int c0;              // first column of the supernode (forest index): input rows Wk[c0 .. c0+klen)
+  int row0;            // first row of the slice inside the supernode (multiple of 32)
+  int w, h;            // supernode width / height
+  int pad_;
+};
+
+struct BwdPanel {      // one 32-row slice of M_s^T
+  long long off;       // offset into bwd_data
+  long long rows_off;  // offset into rows (forest row index of each supernode row)
+  int klen;            // number of k steps (even), covering supernode rows [k0, k0+klen) (clipped at h)
+  int k0;              // = row0 (multiple of 32): first supernode row that contributes
+  int c0;              // first column of the supernode
+  int w, h;
+  int pad_;
+};
+
+struct WorkUnit {      // one CTA of the sweep kernels
+  int first;           // first panel
+  int count;           // 1..8 panels (one per warp), or 1 panel split over all warps when split != 0
+  int split;
+  int pad_;
+};
+
+}  // namespace pcu
+
+struct pcu_bj {
+  pcu_ctx* ctx = nullptr;
+  int n = 0;           // total rows over all local blocks
+  int nblk = 0;
+  int nsuper = 0, nlevels = 0;
+  long long nu = 0;    // rows of the update buffer = sum (h - w)
+  double stat[16] = {0};
+  // device: factor
+  double* fwd_data = nullptr;
+  double* bwd_data = nullptr;
+  long long fwd_doubles = 0, bwd_doubles = 0;
+  pcu::FwdPanel* fwd_panels = nullptr;
+  pcu::BwdPanel* bwd_panels = nullptr;
+  pcu::WorkUnit* fwd_units = nullptr;
+  pcu::WorkUnit* bwd_units = nullptr;
+  std::vector<int> fwd_unit_ptr, bwd_unit_ptr;   // per level, nlevels+1
+  // device: assembly of the forward right-hand side
+  int* perm = nullptr;             // perm[forest col] = local row of the m x t block
+  int* rows = nullptr;             // forest row index of every supernode row (gather index of the backward sweep)
+  int* lvl_cols = nullptr;         // forest columns sorted by level
+  std::vector<int> lvl_col_ptr;    // per level, nlevels+1
+  long long* gl_ptr = nullptr;     // per forest column: range into gl_idx
+  long long* gl_idx = nullptr;     // rows of U that must be subtracted from that column
+  // work vectors (sized for cap_t columns)
+  int cap_t = 0;
+  double* Wk = nullptr;
+  double* Y = nullptr;
+  double* U = nullptr;
+  double* Xp = nullptr;            // solution in forest (permuted) order, read by the descendants
+};

@@ -1,0 +1,349 @@
+// spmm.cu -- K1: CSR SpMM over the m x t enlarged block, plus the halo pack/exchange.
+//
+// Y = A_loc * [X ; H].  Replaces mkl_dcsrmm as driven by CPLM_MatCSRMatMult_v2
+// (ref: utils/cplm_v0/cplm_v0_matmult_v2.c:108-343, utils/cplm_light/cplm_kernels.c:620-671).
+//
+// Kernel shape (HBM-bound, see DESIGN.md "SpMM"):
+//   * a CTA owns a contiguous row block whose col/val stream (<= kNnzCap entries)
+//     is one contiguous chunk of the CSR arrays: it is staged into shared memory
+//     with fully coalesced loads, so the 12 B/nnz stream is read from HBM exactly
+//     once and never at sub-sector granularity;
+//   * a group of G = T/2 lanes owns one row (vector-per-lane: each lane keeps two
+//     adjacent columns in a double2), walks that row's entries out of shared
+//     memory (broadcast reads) and gathers the T-wide row-major X rows with
+//     128-bit loads, i.e. one 16*G-byte contiguous segment per non-zero;
+//   * no atomics, no cross-lane reduction: fixed summation order per row
+//     (ascending column), bit-reproducible.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kNnzCap = 3072;   // staged entries per CTA: 36 KB of shared memory
+constexpr int kRowCap = 256;
+
+struct SpmmArgs {
+  const int* rowPtr;
+  const int* colInd;
+  const double* val;
+  const int* blk;  // row-block boundaries, nblk+1
+  int m;
+  const double* X;
+  int ldx;
+  const double* H;  // halo rows, ld = t
+  double* Y;
+  int ldy;
+  int t;
+};
+
+__device__ __forceinline__ double2 ldg2(const double* p) {
+  return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// T columns, G lanes per row, each lane owns columns {2*lig, 2*lig+1} (T >= 2) or column 0 (T == 1).
+template <int T>
+__global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
+  constexpr int CPL = (T >= 2) ? 2 : 1;
+  constexpr int G = T / CPL;
+  constexpr int NG = kThreads / G;
+  __shared__ int s_col[kNnzCap];
+  __shared__ double s_val[kNnzCap];
+  __shared__ int s_rp[kRowCap + 1];
+
+  const int r0 = a.blk[blockIdx.x], r1 = a.blk[blockIdx.x + 1];
+  const int p0 = a.rowPtr[r0], p1 = a.rowPtr[r1];
+  const int n = p1 - p0;
+  const int tid = threadIdx.x;
+
+  if (n <= kNnzCap) {
+    for (int i = tid; i < n; i += kThreads) {
+      s_col[i] = __ldg(a.colInd + p0 + i);
+      s_val[i] = __ldg(a.val + p0 + i);
+    }
+    for (int i = tid; i <= r1 - r0; i += kThreads) s_rp[i] = __ldg(a.rowPtr + r0 + i) - p0;
+    __syncthreads();
+    const int grp = tid / G, lig = tid % G;
+    for (int r = r0 + grp; r < r1; r += NG) {
+      const int b = s_rp[r - r0], e = s_rp[r - r0 + 1];
+      double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 4
+      for (int p = b; p < e; ++p) {
+        const int c = s_col[p];
+        const double v = s_val[p];
+        const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * a.t;
+        if (CPL == 2) {
+          const double2 x = ldg2(src + 2 * lig);
+          acc0 = fma(v, x.x, acc0);
+          acc1 = fma(v, x.y, acc1);
+        } else {
+          acc0 = fma(v, __ldg(src), acc0);
+        }
+      }
+      double* dst = a.Y + (size_t)r * a.ldy;
+      if (CPL == 2) *reinterpret_cast<double2*>(dst + 2 * lig) = make_double2(acc0, acc1);
+      else dst[0] = acc0;
+    }
+  } else {
+    // a single very long row (the host never puts two rows in an oversized block):
+    // all threads stride over it, then a fixed-order tree reduction in shared memory.
+    double* red = s_val;  // kNnzCap >= kThreads * 2
+    const int r = r0;
+    for (int c0 = 0; c0 < T; c0 += 2) {
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int p = p0 + tid; p < p1; p += kThreads) {
+        const int c = a.colInd[p];
+        const double v = a.val[p];
+        const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * a.t;
+        acc0 = fma(v, src[c0], acc0);
+        if (c0 + 1 < T) acc1 = fma(v, src[c0 + 1], acc1);
+      }
+      red[tid] = acc0;
+      red[kThreads + tid] = acc1;
+      __syncthreads();
+      for (int s = kThreads / 2; s > 0; s >>= 1) {
+        if (tid < s) { red[tid] += red[tid + s]; red[kThreads + tid] += red[kThreads + tid + s]; }
+        __syncthreads();
+      }
+      if (tid == 0) {
+        a.Y[(size_t)r * a.ldy + c0] = red[0];
+        if (c0 + 1 < T) a.Y[(size_t)r * a.ldy + c0 + 1] = red[kThreads];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// any 1 <= t <= 32: 16 lanes per row, lane owns columns lig and lig+16
+__global__ void __launch_bounds__(kThreads) spmm_kernel_generic(SpmmArgs a) {
+  constexpr int G = 16, NG = kThreads / G;
+  __shared__ int s_col[kNnzCap];
+  __shared__ double s_val[kNnzCap];
+  const int r0 = a.blk[blockIdx.x], r1 = a.blk[blockIdx.x + 1];
+  const int tid = threadIdx.x, grp = tid / G, lig = tid % G;
+  const int t = a.t;
+  // rows are processed in sub-blocks that fit the staging buffers
+  for (int rs = r0; rs < r1;) {
+    int re = rs;
+    const int p0 = a.rowPtr[rs];
+    while (re < r1 && a.rowPtr[re + 1] - p0 <= kNnzCap) ++re;
+    if (re == rs) {  // one row longer than the buffer: direct global reads
+      const int p1 = a.rowPtr[rs + 1];
+      if (grp == 0) {
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int p = p0; p < p1; ++p) {
+          const int c = a.colInd[p];
+          const double v = a.val[p];
+          const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * t;
+          if (lig < t) acc0 = fma(v, src[lig], acc0);
+          if (lig + 16 < t) acc1 = fma(v, src[lig + 16], acc1);
+        }
+        if (lig < t) a.Y[(size_t)rs * a.ldy + lig] = acc0;
+        if (lig + 16 < t) a.Y[(size_t)rs * a.ldy + lig + 16] = acc1;
+      }
+      rs += 1;
+      continue;
+    }
+    const int n = a.rowPtr[re] - p0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kThreads) { s_col[i] = a.colInd[p0 + i]; s_val[i] = a.val[p0 + i]; }
+    __syncthreads();
+    for (int r = rs + grp; r < re; r += NG) {
+      const int b = a.rowPtr[r] - p0, e = a.rowPtr[r + 1] - p0;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int p = b; p < e; ++p) {
+        const int c = s_col[p];
+        const double v = s_val[p];
+        const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * t;
+        if (lig < t) acc0 = fma(v, __ldg(src + lig), acc0);
+        if (lig + 16 < t) acc1 = fma(v, __ldg(src + lig + 16), acc1);
+      }
+      if (lig < t) a.Y[(size_t)r * a.ldy + lig] = acc0;
+      if (lig + 16 < t) a.Y[(size_t)r * a.ldy + lig + 16] = acc1;
+    }
+    rs = re;
+  }
+}
+
+__global__ void halo_pack_kernel(const double* __restrict__ X, int ldx, int t, const int* __restrict__ idx,
+                                 int nrows, double* __restrict__ out) {
+  const int64_t total = (int64_t)nrows * t;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / t), c = (int)(i % t);
+    out[i] = X[(size_t)idx[r] * ldx + c];
+  }
+}
+
+}  // namespace
+
+struct pcu_spmm {
+  pcu_ctx* ctx = nullptr;
+  int m = 0, nhalo = 0;
+  int64_t nnz = 0;
+  int* d_rowPtr = nullptr;
+  int* d_colInd = nullptr;
+  double* d_val = nullptr;
+  int* d_blk = nullptr;
+  int nblk = 0;
+  bool vec_ok = true;  // all row blocks fit the staging buffers or are single rows
+  // halo
+  int nnbr = 0;
+  std::vector<int> nbr_rank, send_ptr, recv_ptr;
+  int* d_send_idx = nullptr;
+  int nsend = 0;
+  double* d_sendbuf = nullptr;
+  double* d_halo = nullptr;
+  int buf_t = 0;  // width the halo/send buffers are currently sized for
+};
+
+using namespace pcu;
+
+static int ensure_halo_buffers(pcu_spmm* op, int t) {
+  if (op->buf_t >= t) return 0;
+  pcu_ctx* c = op->ctx;
+  PCU_CUDA(cudaStreamSynchronize(c->stream));
+  if (op->d_sendbuf) cudaFree(op->d_sendbuf);
+  if (op->d_halo) cudaFree(op->d_halo);
+  op->d_sendbuf = op->d_halo = nullptr;
+  const int tt = std::max(t, 8);
+  PCU_CUDA(cudaMalloc(&op->d_sendbuf, sizeof(double) * (size_t)std::max(op->nsend, 1) * tt));
+  PCU_CUDA(cudaMalloc(&op->d_halo, sizeof(double) * (size_t)std::max(op->nhalo, 1) * tt));
+  op->buf_t = tt;
+  return 0;
+}
+
+extern "C" {
+
+int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int* colInd,
+                    const double* val, pcu_spmm** out) {
+  PCU_CHECK(ctx && rowPtr && colInd && val && out && m >= 0 && nhalo >= 0, "pcu_spmm_create: bad arguments");
+  PCU_CUDA(cudaSetDevice(ctx->device));
+  pcu_spmm* op = new pcu_spmm();
+  op->ctx = ctx;
+  op->m = m;
+  op->nhalo = nhalo;
+  op->nnz = rowPtr[m];
+  for (int64_t p = 0; p < op->nnz; ++p)
+    PCU_CHECK(colInd[p] >= 0 && colInd[p] < m + nhalo, "pcu_spmm_create: column index %d out of range at %lld",
+              colInd[p], (long long)p);
+  // row blocks: <= kRowCap rows and <= kNnzCap entries; an over-long row gets a block of its own
+  std::vector<int> blk;
+  blk.push_back(0);
+  for (int r = 0; r < m;) {
+    int e = r;
+    while (e < m && e - r < kRowCap && rowPtr[e + 1] - rowPtr[r] <= kNnzCap) ++e;
+    if (e == r) e = r + 1;
+    blk.push_back(e);
+    r = e;
+  }
+  op->nblk = (int)blk.size() - 1;
+  PCU_CUDA(cudaMalloc(&op->d_rowPtr, sizeof(int) * (size_t)(m + 1)));
+  PCU_CUDA(cudaMalloc(&op->d_colInd, sizeof(int) * (size_t)std::max<int64_t>(op->nnz, 1)));
+  PCU_CUDA(cudaMalloc(&op->d_val, sizeof(double) * (size_t)std::max<int64_t>(op->nnz, 1)));
+  PCU_CUDA(cudaMalloc(&op->d_blk, sizeof(int) * blk.size()));
+  PCU_CUDA(cudaMemcpy(op->d_rowPtr, rowPtr, sizeof(int) * (size_t)(m + 1), cudaMemcpyHostToDevice));
+  PCU_CUDA(cudaMemcpy(op->d_colInd, colInd, sizeof(int) * (size_t)op->nnz, cudaMemcpyHostToDevice));
+  PCU_CUDA(cudaMemcpy(op->d_val, val, sizeof(double) * (size_t)op->nnz, cudaMemcpyHostToDevice));
+  PCU_CUDA(cudaMemcpy(op->d_blk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice));
+  *out = op;
+  return 0;
+}
+
+int pcu_spmm_destroy(pcu_spmm* op) {
+  if (!op) return 0;
+  cudaSetDevice(op->ctx->device);
+  cudaStreamSynchronize(op->ctx->stream);
+  cudaFree(op->d_rowPtr); cudaFree(op->d_colInd); cudaFree(op->d_val); cudaFree(op->d_blk);
+  if (op->d_send_idx) cudaFree(op->d_send_idx);
+  if (op->d_sendbuf) cudaFree(op->d_sendbuf);
+  if (op->d_halo) cudaFree(op->d_halo);
+  delete op;
+  return 0;
+}
+
+int pcu_spmm_set_halo(pcu_spmm* op, int nnbr, const int* nbr_rank, const int* send_ptr,
+                      const int* send_idx, const int* recv_ptr) {
+  PCU_CHECK(op && nnbr >= 0, "pcu_spmm_set_halo: bad arguments");
+  op->nnbr = nnbr;
+  op->nbr_rank.assign(nbr_rank, nbr_rank + nnbr);
+  op->send_ptr.assign(send_ptr, send_ptr + nnbr + 1);
+  op->recv_ptr.assign(recv_ptr, recv_ptr + nnbr + 1);
+  op->nsend = nnbr ? send_ptr[nnbr] : 0;
+  PCU_CHECK((nnbr ? recv_ptr[nnbr] : 0) == op->nhalo, "pcu_spmm_set_halo: recv_ptr covers %d rows, halo has %d",
+            nnbr ? recv_ptr[nnbr] : 0, op->nhalo);
+  for (int i = 0; i < op->nsend; ++i)
+    PCU_CHECK(send_idx[i] >= 0 && send_idx[i] < op->m, "pcu_spmm_set_halo: send index out of range");
+  if (op->d_send_idx) { cudaFree(op->d_send_idx); op->d_send_idx = nullptr; }
+  PCU_CUDA(cudaMalloc(&op->d_send_idx, sizeof(int) * (size_t)std::max(op->nsend, 1)));
+  if (op->nsend) PCU_CUDA(cudaMemcpy(op->d_send_idx, send_idx, sizeof(int) * (size_t)op->nsend, cudaMemcpyHostToDevice));
+  op->buf_t = 0;
+  return 0;
+}
+
+double* pcu_spmm_halo_buffer(pcu_spmm* op, int t) {
+  if (ensure_halo_buffers(op, t)) return nullptr;
+  return op->d_halo;
+}
+
+int pcu_spmm_halo_pack(pcu_spmm* op, const double* X, int ldx, int t, double** packed_dev, int* nrows) {
+  if (ensure_halo_buffers(op, t)) return 1;
+  pcu_ctx* c = op->ctx;
+  if (op->nsend > 0) {
+    const int grid = stream_grid(c, (int64_t)op->nsend * t, 256, 4);
+    halo_pack_kernel<<<grid, 256, 0, c->stream>>>(X, ldx, t, op->d_send_idx, op->nsend, op->d_sendbuf);
+    PCU_LAUNCH_CHECK(c);
+  }
+  if (packed_dev) *packed_dev = op->d_sendbuf;
+  if (nrows) *nrows = op->nsend;
+  return 0;
+}
+
+int pcu_spmm_halo_exchange(pcu_spmm* op, const double* X, int ldx, int t) {
+  pcu_ctx* c = op->ctx;
+  if (op->nnbr == 0) return 0;
+  PCU_CHECK(c->nccl_comm != nullptr, "pcu_spmm_halo_exchange: %d neighbours but no NCCL communicator", op->nnbr);
+  if (pcu_spmm_halo_pack(op, X, ldx, t, nullptr, nullptr)) return 1;
+  if (nccl_group_start(c)) return 1;
+  for (int q = 0; q < op->nnbr; ++q) {
+    const int ns = op->send_ptr[q + 1] - op->send_ptr[q], nr = op->recv_ptr[q + 1] - op->recv_ptr[q];
+    if (ns > 0 && nccl_send(c, op->d_sendbuf + (size_t)op->send_ptr[q] * t, (size_t)ns * t, 1, op->nbr_rank[q])) return 1;
+    if (nr > 0 && nccl_recv(c, op->d_halo + (size_t)op->recv_ptr[q] * t, (size_t)nr * t, 1, op->nbr_rank[q])) return 1;
+  }
+  if (nccl_group_end(c)) return 1;
+  return 0;
+}
+
+int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, int t) {
+  PCU_CHECK(op && X && Y && t >= 1, "pcu_spmm_apply: bad arguments");
+  PCU_CHECK(X != Y, "pcu_spmm_apply: X and Y must not alias");
+  pcu_ctx* c = op->ctx;
+  if (op->m == 0) return 0;
+  if (op->nhalo > 0 && ensure_halo_buffers(op, t)) return 1;
+  PCU_CHECK(t <= 32, "pcu_spmm_apply: t=%d > 32 is not supported", t);
+  SpmmArgs a{op->d_rowPtr, op->d_colInd, op->d_val, op->d_blk, op->m, X, ldx, op->d_halo, Y, ldy, t};
+  const bool aligned = (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0);
+  const bool pow2 = (t == 2 || t == 4 || t == 8 || t == 16 || t == 32);
+  if (t == 1) spmm_kernel<1><<<op->nblk, kThreads, 0, c->stream>>>(a);
+  else if (aligned && pow2) {
+    switch (t) {
+      case 2: spmm_kernel<2><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      case 4: spmm_kernel<4><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      case 8: spmm_kernel<8><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      case 16: spmm_kernel<16><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      default: spmm_kernel<32><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+    }
+  } else {
+    spmm_kernel_generic<<<op->nblk, kThreads, 0, c->stream>>>(a);
+  }
+  PCU_LAUNCH_CHECK(c);
+  return 0;
+}
+
+double pcu_spmm_bytes(pcu_spmm* op, int t) {
+  // nnz*(8+4) + (m+1)*4 + read X once + write Y once (+ halo rows read once)
+  return (double)op->nnz * 12.0 + (double)(op->m + 1) * 4.0 + 2.0 * (double)op->m * t * 8.0 +
+         (double)op->nhalo * t * 8.0;
+}
+
+}  // extern "C"

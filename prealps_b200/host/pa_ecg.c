@@ -1,0 +1,347 @@
+/*
+ * pa_ecg.c -- preAlps_ECG* reverse-communication solver (ref: src/solvers/ecg.c:41-728).
+ *
+ * Control flow, stopping rule and protocol are the reference's; the numerics run as three
+ * fused streaming passes per iteration on device-resident ROW_MAJOR blocks
+ * (include/prealps_cuda.h):
+ *   Iterate(rci 0), ref ecg.c:421-507:
+ *     pass 1  G = AP^T P and Gpr = P^T R in one sweep            (pcu_gram2)
+ *     one all-reduce of 2 t^2 doubles (the reference does two: ecg.c:427 and :441)
+ *     pass 2  U = chol(G); P,AP <- .U^{-1}; alpha = U^{-T} Gpr; X += P alpha; R -= AP alpha;
+ *             ||R||_F^2                                         (pcu_ortho_update)
+ *   StoppingCriterion, ref ecg.c:223-271: res = sqrt(trace(R^T R)) -- the squared Frobenius norm
+ *     was produced by pass 2, so only its all-reduce and an 8-byte read-back remain
+ *   Iterate(rci 1), ref ecg.c:508-527:
+ *     pass 3  beta = [AP^T Z ; APprev^T Z]                       (pcu_gram2), all-reduce 2 t^2
+ *     pass 4  Z -= P beta1 + Pprev beta2                         (pcu_update_z)
+ *     the three block copies of ecg.c:521-523 become a pointer rotation.
+ * alpha = U^{-T}(P_old^T R) equals (P U^{-1})^T R of the reference in exact arithmetic; the
+ * rounding differs at the 1e-16 level ("parity").
+ */
+#include "pa_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+  preAlps_ECG_t* owner;
+  int m, t, ld;
+  double* buf[7];       /* P, Pprev, AP, APprev, Z, R, X (roles rotate, see rotate()) */
+  double *P, *Pp, *AP, *APp, *Z, *R, *X;
+  double* small;        /* G | Gpr | U | alpha | beta1 | beta2 | rr_local | rr_glob */
+  double* rhs_dev;
+  int* col_of_row;
+  int* status_dev;
+  int have_rr;
+  int iter_since_reset;
+} ecg_priv_t;
+
+#define MAX_SOLVERS 16
+static ecg_priv_t* g_priv[MAX_SOLVERS];
+
+static ecg_priv_t* priv_of(preAlps_ECG_t* ecg) {
+  for (int i = 0; i < MAX_SOLVERS; ++i) if (g_priv[i] && g_priv[i]->owner == ecg) return g_priv[i];
+  return NULL;
+}
+
+static double* sm_G(ecg_priv_t* p) { return p->small; }
+static double* sm_Gpr(ecg_priv_t* p) { return p->small + (size_t)p->t * p->t; }
+static double* sm_U(ecg_priv_t* p) { return p->small + 2 * (size_t)p->t * p->t; }
+static double* sm_alpha(ecg_priv_t* p) { return p->small + 3 * (size_t)p->t * p->t; }
+static double* sm_beta1(ecg_priv_t* p) { return p->small + 4 * (size_t)p->t * p->t; }
+static double* sm_beta2(ecg_priv_t* p) { return p->small + 5 * (size_t)p->t * p->t; }
+static double* sm_rr(ecg_priv_t* p) { return p->small + 6 * (size_t)p->t * p->t; }
+
+static void set_shell(CPLM_Mat_Dense_t* s, double* val, int M, int m, int n, int ld) {
+  CPLM_MatDenseSetInfo(s, M, n, m, n, ROW_MAJOR);
+  s->info.lda = ld;
+  s->val = val;
+}
+
+static void refresh_shells(preAlps_ECG_t* ecg, ecg_priv_t* p) {
+  const int M = ecg->globPbSize, m = p->m, bs = ecg->bs > 0 ? ecg->bs : p->t;
+  set_shell(ecg->X, p->X, M, m, p->t, p->ld);
+  set_shell(ecg->R, p->R, M, m, p->t, p->ld);
+  set_shell(ecg->P, p->P, M, m, bs, p->ld);
+  set_shell(ecg->AP, p->AP, M, m, bs, p->ld);
+  set_shell(ecg->V, p->P, M, m, bs, p->ld);
+  set_shell(ecg->AV, p->AP, M, m, bs, p->ld);
+  set_shell(ecg->Z, p->Z, M, m, bs, p->ld);
+  ecg->P_p = p->P; ecg->AP_p = p->AP; ecg->R_p = p->R; ecg->Z_p = p->Z;
+}
+
+int _preAlps_ECGMalloc(preAlps_ECG_t* ecg) {
+  pcu_ctx* c = pa_ctx();
+  const int m = ecg->locPbSize, t = ecg->enlFac;
+  if (t < 1 || t > 32) CPLM_Abort("enlarging factor %d is outside the supported range 1..32", t);
+  ecg_priv_t* p = (ecg_priv_t*)pa_xcalloc(1, sizeof(ecg_priv_t));
+  int slot = -1;
+  for (int i = 0; i < MAX_SOLVERS; ++i) if (!g_priv[i]) { slot = i; break; }
+  if (slot < 0) CPLM_Abort("too many live ECG solvers");
+  g_priv[slot] = p;
+  p->owner = ecg; p->m = m; p->t = t;
+  p->ld = (t % 2 == 0 || t == 1) ? t : t + 1;  /* even row stride keeps 16-byte vector access legal */
+  const size_t blk = (size_t)m * p->ld;
+  const size_t smalls = 6 * (size_t)t * t + 16;
+  /* one pool, like the reference's mkl_calloc(7mt + 3t^2) (ref: ecg.c:58-62), but in HBM */
+  ecg->work = (double*)pcu_malloc(c, sizeof(double) * (7 * blk + smalls + 8));
+  if (!ecg->work) CPLM_Abort("device allocation of the ECG pool failed: %s", pcu_last_error());
+  pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * (7 * blk + smalls + 8)), "pcu_memset");
+  for (int i = 0; i < 7; ++i) p->buf[i] = ecg->work + (size_t)i * blk;
+  p->small = ecg->work + 7 * blk;
+  p->rhs_dev = (double*)pcu_malloc(c, sizeof(double) * (size_t)(m > 0 ? m : 1));
+  p->col_of_row = (int*)pcu_malloc(c, sizeof(int) * (size_t)(m > 0 ? m : 1));
+  p->status_dev = (int*)pcu_malloc(c, sizeof(int) * 4);
+  if (!p->rhs_dev || !p->col_of_row || !p->status_dev) CPLM_Abort("device allocation failed: %s", pcu_last_error());
+  ecg->iwork = (int*)pa_xcalloc((size_t)t, sizeof(int));
+  ecg->X = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->R = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->V = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->AV = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->Z = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->alpha = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->beta = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->P = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  ecg->AP = (CPLM_Mat_Dense_t*)pa_xcalloc(1, sizeof(CPLM_Mat_Dense_t));
+  return 0;
+}
+
+int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
+  ecg_priv_t* p = priv_of(ecg);
+  if (!p) CPLM_Abort("_preAlps_ECGReset on a solver that was not allocated");
+  pcu_ctx* c = pa_ctx();
+  pa_state_t* g = &pa_g;
+  ecg->tot_t = ecg->comm_t = ecg->trsm_t = ecg->gemm_t = ecg->potrf_t = ecg->pstrf_t = 0.0;
+  ecg->lapmt_t = ecg->gesvd_t = ecg->geqrf_t = ecg->ormqr_t = ecg->copy_t = 0.0;
+  const int m = p->m, t = p->t;
+  const size_t blk = (size_t)m * p->ld;
+  p->P = p->buf[0]; p->Pp = p->buf[1]; p->AP = p->buf[2]; p->APp = p->buf[3];
+  p->Z = p->buf[4]; p->R = p->buf[5]; p->X = p->buf[6];
+  pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * 7 * blk), "pcu_memset");
+  /* ||b||: per-subdomain sums in row order, then summed over subdomains/processes (ref: ecg.c:143-155) */
+  double nb = 0.0;
+  int* cor = (int*)pa_xmalloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
+  const int nsub = g->built ? g->s_hi - g->s_lo : 1;
+  for (int s = 0; s < nsub; ++s) {
+    const int r0 = g->built ? g->rowPos[g->s_lo + s] - g->g0 : 0;
+    const int r1 = g->built ? g->rowPos[g->s_lo + s + 1] - g->g0 : m;
+    double part = 0.0;
+    for (int i = r0; i < r1; ++i) part += pow(rhs[i], 2);
+    nb += part;
+    /* R0 = T(b): the rows of subdomain s feed column s % t (ref: ecg.c:162 with rank -> subdomain id) */
+    const int col = ((g->built ? g->s_lo : g->rank) + s) % t;
+    for (int i = r0; i < r1; ++i) cor[i] = col;
+  }
+  if (g->nproc > 1 && g->xport == PA_XPORT_MPI) {
+    const double t0 = pa_wtime();
+    MPI_Allreduce(MPI_IN_PLACE, &nb, 1, MPI_DOUBLE, MPI_SUM, ecg->comm);
+    ecg->comm_t += pa_wtime() - t0;
+  } else if (g->nproc > 1 && g->xport == PA_XPORT_NCCL) {
+    pa_cuda_check(pcu_h2d(c, sm_rr(p), &nb, sizeof(double)), "pcu_h2d");
+    pa_allreduce_dev(sm_rr(p), 1, &ecg->comm_t);
+    pa_cuda_check(pcu_d2h(c, &nb, sm_rr(p), sizeof(double)), "pcu_d2h");
+  }
+  ecg->normb = sqrt(nb);
+  ecg->res = 1.0;
+  ecg->iter = 0;
+  ecg->bs = t;
+  ecg->kbs = (ecg->ortho_alg == ORTHOMIN) ? t : 2 * t;
+  pa_cuda_check(pcu_h2d(c, p->rhs_dev, rhs, sizeof(double) * (size_t)m), "pcu_h2d");
+  pa_cuda_check(pcu_h2d(c, p->col_of_row, cor, sizeof(int) * (size_t)m), "pcu_h2d");
+  free(cor);
+  pa_cuda_check(pcu_split_rhs(c, m, t, p->rhs_dev, p->col_of_row, p->R, p->ld), "pcu_split_rhs");
+  refresh_shells(ecg, p);
+  CPLM_MatDenseSetInfo(ecg->alpha, t, t, t, t, COL_MAJOR);
+  ecg->alpha->val = sm_alpha(p);
+  CPLM_MatDenseSetInfo(ecg->beta, ecg->kbs, t, ecg->kbs, t, COL_MAJOR);
+  ecg->beta->val = sm_beta1(p);
+  p->have_rr = 0;
+  p->iter_since_reset = 0;
+  *rci_request = 0;
+  return 0;
+}
+
+int preAlps_ECGInitialize(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
+  /* the reference requires #ranks >= enlFac (ref: ecg.c:178-183); with virtual subdomains the
+   * number that matters is the number of METIS subdomains */
+  int size = pa_g.built ? pa_g.S : 1;
+  if (!pa_g.built) MPI_Comm_size(ecg->comm, &size);
+  if (size < ecg->enlFac)
+    CPLM_Abort("Enlarging factor must be lower than the number of processors in the MPI communicator! size: %d ; enlarging factor: %d",
+               size, ecg->enlFac);
+  if (ecg->bs_red == ADAPT_BS)
+    CPLM_Abort("adaptive reduction of the search directions (-r 1) is not implemented in this build yet");
+  if (ecg->ortho_alg == ORTHODIR_FUSED)
+    CPLM_Abort("ORTHODIR_FUSED is not implemented in this build yet (ORTHODIR already needs one all-reduce per half step)");
+  _preAlps_ECGMalloc(ecg);
+  return _preAlps_ECGReset(ecg, rhs, rci_request);
+}
+
+static void check_status(preAlps_ECG_t* ecg, ecg_priv_t* p) {
+  if (ecg->ortho_alg != ORTHOMIN) return;  /* Orthodir ignores dpotrf's return code (ref: ecg.c:431) */
+  int st = 0;
+  pa_cuda_check(pcu_d2h(pa_g.ctx, &st, p->status_dev, sizeof(int)), "pcu_d2h");
+  if (st != 0) CPLM_Abort("ACHQR: dpotrf:\n ERROR: P^tAP is not spd!");  /* ref: ecg.c:320-322 */
+}
+
+/* shared by Orthodir and Orthomin: ref ecg.c:421-443,499-506 == ecg.c:307-343 */
+static void descent_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, t = ecg->bs, ld = p->ld;
+  double t0 = pa_wtime();
+  pa_cuda_check(pcu_gram2(c, m, t, p->AP, ld, p->P, ld, sm_G(p), p->P, ld, p->R, ld, sm_Gpr(p)), "pcu_gram2");
+  ecg->gemm_t += pa_wtime() - t0;
+  pa_allreduce_dev(sm_G(p), 2 * p->t * p->t, &ecg->comm_t);  /* G and Gpr are adjacent */
+  t0 = pa_wtime();
+  pa_cuda_check(pcu_ortho_update(c, m, t, sm_G(p), sm_Gpr(p), p->P, ld, p->AP, ld, p->X, ld, p->R, ld, sm_U(p),
+                                 sm_alpha(p), sm_rr(p), p->status_dev),
+                "pcu_ortho_update");
+  ecg->trsm_t += pa_wtime() - t0;
+  check_status(ecg, p);
+  p->have_rr = 1;
+  ecg->iter++;
+  p->iter_since_reset++;
+}
+
+int _preAlps_ECGIterateOdir(preAlps_ECG_t* ecg, int* rci_request) {
+  ecg_priv_t* p = priv_of(ecg);
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, t = ecg->bs, ld = p->ld;
+  if (*rci_request == 0) {
+    descent_half_step(ecg, p);
+    *rci_request = 1;
+  } else if (*rci_request == 1) {
+    double t0 = pa_wtime();
+    pa_cuda_check(pcu_gram2(c, m, t, p->AP, ld, p->Z, ld, sm_beta1(p), p->APp, ld, p->Z, ld, sm_beta2(p)), "pcu_gram2");
+    ecg->gemm_t += pa_wtime() - t0;
+    pa_allreduce_dev(sm_beta1(p), 2 * p->t * p->t, &ecg->comm_t);
+    t0 = pa_wtime();
+    pa_cuda_check(pcu_update_z(c, m, t, p->Z, ld, p->P, ld, t, sm_beta1(p), p->Pp, ld, t, sm_beta2(p)), "pcu_update_z");
+    ecg->gemm_t += pa_wtime() - t0;
+    /* ref: ecg.c:521-523 copies P -> P_prev, AP -> AP_prev, Z -> P; here the buffers trade roles */
+    t0 = pa_wtime();
+    double* oldPp = p->Pp; double* oldAPp = p->APp;
+    p->Pp = p->P; p->P = p->Z; p->Z = oldPp;
+    p->APp = p->AP; p->AP = oldAPp;
+    refresh_shells(ecg, p);
+    ecg->copy_t += pa_wtime() - t0;
+    *rci_request = 0;
+  }
+  return 0;
+}
+
+int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
+  ecg_priv_t* p = priv_of(ecg);
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, t = ecg->bs, ld = p->ld;
+  if (*rci_request == 0) {
+    descent_half_step(ecg, p);
+    *rci_request = 1;
+  } else if (*rci_request == 1) {
+    /* beta = AP^T Z ; Z -= P beta ; P <- Z   (ref: ecg.c:345-359) */
+    double t0 = pa_wtime();
+    pa_cuda_check(pcu_gram2(c, m, t, p->AP, ld, p->Z, ld, sm_beta1(p), NULL, 0, NULL, 0, NULL), "pcu_gram2");
+    ecg->gemm_t += pa_wtime() - t0;
+    pa_allreduce_dev(sm_beta1(p), p->t * p->t, &ecg->comm_t);
+    t0 = pa_wtime();
+    pa_cuda_check(pcu_update_z(c, m, t, p->Z, ld, p->P, ld, t, sm_beta1(p), NULL, 0, 0, NULL), "pcu_update_z");
+    ecg->gemm_t += pa_wtime() - t0;
+    double* oldP = p->P;
+    p->P = p->Z; p->Z = oldP;
+    refresh_shells(ecg, p);
+    *rci_request = 0;
+  }
+  return 0;
+}
+
+int _preAlps_ECGIterateOdirFused(preAlps_ECG_t* ecg, int* rci_request) {
+  (void)ecg; (void)rci_request;
+  CPLM_Abort("ORTHODIR_FUSED is not implemented in this build yet");
+  return 1;
+}
+
+int preAlps_ECGIterate(preAlps_ECG_t* ecg, int* rci_request) {
+  const double t0 = pa_wtime();
+  if (ecg->ortho_alg == ORTHOMIN) _preAlps_ECGIterateOmin(ecg, rci_request);
+  else if (ecg->ortho_alg == ORTHODIR) _preAlps_ECGIterateOdir(ecg, rci_request);
+  else _preAlps_ECGIterateOdirFused(ecg, rci_request);
+  ecg->tot_t += pa_wtime() - t0;
+  return 0;
+}
+
+int preAlps_ECGStoppingCriterion(preAlps_ECG_t* ecg, int* stop) {
+  const double t0 = pa_wtime();
+  ecg_priv_t* p = priv_of(ecg);
+  pcu_ctx* c = pa_g.ctx;
+  if (!stop) CPLM_Abort(" wrong test 'stop != NULL'");
+  if (!p->have_rr) {  /* R changed outside Iterate (or first call): one pass over R */
+    const double tg = pa_wtime();
+    pa_cuda_check(pcu_fro2(c, p->m, p->t, p->R, p->ld, sm_rr(p)), "pcu_fro2");
+    ecg->gemm_t += pa_wtime() - tg;
+    p->have_rr = 1;
+  }
+  double* rr_glob = sm_rr(p) + 1;
+  pa_cuda_check(pcu_d2d(c, rr_glob, sm_rr(p), sizeof(double)), "pcu_d2d");
+  pa_allreduce_dev(rr_glob, 1, &ecg->comm_t);
+  double rr = 0.0;
+  pa_cuda_check(pcu_d2h(c, &rr, rr_glob, sizeof(double)), "pcu_d2h");
+  ecg->res = sqrt(rr);
+  /* ref: ecg.c:264 */
+  if (ecg->res > ecg->normb * ecg->tol && ecg->iter < ecg->maxIter && ecg->bs > 0) *stop = 0;
+  else *stop = 1;
+  ecg->tot_t += pa_wtime() - t0;
+  return 0;
+}
+
+int _preAlps_ECGWrapUp(preAlps_ECG_t* ecg, double* solution) {
+  ecg_priv_t* p = priv_of(ecg);
+  pcu_ctx* c = pa_g.ctx;
+  pa_cuda_check(pcu_sum_columns(c, p->m, p->t, p->X, p->ld, p->rhs_dev), "pcu_sum_columns");
+  pa_cuda_check(pcu_d2h(c, solution, p->rhs_dev, sizeof(double) * (size_t)p->m), "pcu_d2h");
+  return 0;
+}
+
+void _preAlps_ECGFree(preAlps_ECG_t* ecg) {
+  ecg_priv_t* p = priv_of(ecg);
+  pcu_ctx* c = pa_g.ctx;
+  free(ecg->X); free(ecg->R); free(ecg->V); free(ecg->AV); free(ecg->alpha); free(ecg->beta); free(ecg->Z);
+  free(ecg->P); free(ecg->AP);
+  ecg->X = ecg->R = ecg->V = ecg->AV = ecg->alpha = ecg->beta = ecg->Z = ecg->P = ecg->AP = NULL;
+  if (c && ecg->work) pcu_free(c, ecg->work);
+  ecg->work = NULL;
+  free(ecg->iwork); ecg->iwork = NULL;
+  if (p) {
+    if (c) { pcu_free(c, p->rhs_dev); pcu_free(c, p->col_of_row); pcu_free(c, p->status_dev); }
+    for (int i = 0; i < MAX_SOLVERS; ++i) if (g_priv[i] == p) g_priv[i] = NULL;
+    free(p);
+  }
+}
+
+int preAlps_ECGFinalize(preAlps_ECG_t* ecg, double* solution) {
+  const int ierr = _preAlps_ECGWrapUp(ecg, solution);
+  _preAlps_ECGFree(ecg);
+  return ierr;
+}
+
+void preAlps_ECGPrint(preAlps_ECG_t* ecg, int verbosity) {
+  int rank = pa_g.rank;
+  (void)verbosity;
+  printf("[%d] prints ECG_t...\n", rank);
+  printf("=== Summary ===\n");
+  printf("\titer: %d\n\tres : %e\n\tbs  : %1d\n", ecg->iter, ecg->res, ecg->bs);
+  printf("=== Timings ===\n");
+  printf("\ttot_t  : %e s\n", ecg->tot_t);
+  printf("\tcomm_t : %e s\n", ecg->comm_t);
+  printf("\ttrsm_t : %e s\n", ecg->trsm_t);
+  printf("\tgemm_t : %e s\n", ecg->gemm_t);
+  printf("\tpotrf_t: %e s\n", ecg->potrf_t);
+  printf("\tpstrf_t: %e s\n", ecg->pstrf_t);
+  printf("\tlapmt_t: %e s\n", ecg->lapmt_t);
+  printf("\tgesvd_t: %e s\n", ecg->gesvd_t);
+  printf("\tgeqrf_t: %e s\n", ecg->geqrf_t);
+  printf("\tormqr_t: %e s\n", ecg->ormqr_t);
+  printf("\tcopy_t : %e s\n", ecg->copy_t);
+  printf("[%d] ends printing ECG_t!\n", rank);
+}
