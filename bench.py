@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- ECG(t=8) + block-Jacobi on the synthetic 3-D Poisson operator of BASELINE.json.
+
+    python bench.py [--gpus N --steps K --warmup W]          # this library, N processes x 1 GPU (torchrun for N > 1)
+    python bench.py --impl reference [...]                    # the reference's CPU path on the host cores
+
+A "step" is one ECG iteration (SpMM + block-Jacobi apply + the fused dense passes + stopping test) of the
+configs[1] workload: 7-point Poisson 128^3 (2.1 M rows), t = 8, 8 METIS subdomains = 8 block-Jacobi blocks,
+strong-scaled over N GPUs (each GPU owns 8/N consecutive subdomains).  `value` is iterations/s measured with
+CUDA events over exactly K iterations, operands resident in HBM (working set ~17 GB >> the 126 MB L2).  `e2e`
+is the same metric through the reference-facing RCI API with HOST buffers: rhs in, solution out, one 8-byte
+residual read-back per iteration, i.e. iterations / time-to-solution of a whole solve.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+METRIC = "ecg_t8_bjacobi_iterations_per_s"
+UNIT = "iterations/s"
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, as_baseline=False):
+    """The reference's own CPU implementation: the unmodified preAlps sources of oracle/_ref (MKL -> OpenBLAS and a
+    plain-C Cholesky for PARDISO, MPI -> mpishim), 8 ranks x 1 thread, on a bounded sample of the workload."""
+    import numpy as np
+    import gen_matrices
+    exe = os.path.join(ROOT, "oracle", "_ref", "ecg_dump_ref")
+    n_s = args.ref_n
+    cores = min(args.nsub, os.cpu_count() or 1)
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        mtx = os.path.join(d, "A.mtx")
+        gen_matrices.write_mtx(mtx, gen_matrices.poisson7(n_s))
+        env = dict(os.environ, MPISHIM_NP=str(args.nsub))
+        t0 = time.time()
+        subprocess.run([exe, "-m", mtx, "-e", str(args.t), "-o", "0", "-r", "0", "-t", repr(args.tol), "-d", d, "-q"],
+                       check=True, env=env, stdout=subprocess.DEVNULL)
+        wall = time.time() - t0
+        s = json.load(open(os.path.join(d, "summary.json")))
+    it_s_sample = s["iter"] / s["t_solve"]
+    rows_ratio = float(n_s ** 3) / float(args.n ** 3)
+    value = it_s_sample * rows_ratio
+    sample = ("poisson7 %d^3 (%.4g of the rows of %d^3), S=%d ranks x 1 thread (mpishim), t=%d, tol %g: %d iterations in %.2f s "
+              "(SpMM %.2f s, block-Jacobi %.2f s; factorisation %.1f s not counted); iterations/s scaled by the row ratio, "
+              "which favours the CPU (nnz(L) per row grows with the block size)"
+              % (n_s, rows_ratio, args.n, args.nsub, args.t, args.tol, s["iter"], s["t_solve"], s["t_op"], s["t_prec"],
+                 s["t_factor"]))
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+            "sample_iterations_per_s": it_s_sample, "sample_iterations": s["iter"], "wall_s": wall}
+    if as_baseline:
+        return base
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return line
+
+
+def workload_config(args):
+    return {"workload": "synthetic 3D Poisson 7-point %d^3 (%d rows), ECG t=%d + block Jacobi, %d METIS subdomains, tol %g"
+            % (args.n, args.n ** 3, args.t, args.nsub, args.tol),
+            "n": args.n, "t": args.t, "subdomains": args.nsub, "tol": args.tol, "ortho_alg": "ORTHODIR", "bs_red": "NO_BS_RED",
+            "l2": "inputs larger than L2 (factor + blocks ~17 GB per pass); per-kernel timings flush L2 between repetitions"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="grid points per dimension")
+    ap.add_argument("--t", type=int, default=8, help="enlarging factor")
+    ap.add_argument("--nsub", type=int, default=8, help="METIS subdomains = block-Jacobi blocks")
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--ref-n", type=int, default=64, help="grid size of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        line = reference_arm(args)
+        if line is None:
+            line = {"impl": "reference", "unavailable": "oracle/_ref/ecg_dump_ref is not built (make -C oracle needs /root/reference)"}
+        print(json.dumps(line))
+        return 0
+
+    import ctypes as C
+    import numpy as np
+    import torch
+    from prealps_b200 import capi
+
+    if capi.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; this library has no CPU path")
+    if args.nsub % world != 0:
+        raise SystemExit("bench.py: the number of subdomains (%d) must be a multiple of --gpus (%d)" % (args.nsub, world))
+    torch.cuda.set_device(local)
+    capi.lib.preAlps_b200_SetDevice(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            assert capi.lib.preAlps_b200_NcclUniqueId(buf) == 0
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        assert capi.lib.preAlps_b200_InitNccl(world, rank, raw) == 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    per = args.nsub // world
+    t_setup = time.time()
+    assert capi.lib.preAlps_b200_OperatorBuildStencil(0, args.n, args.nsub, rank * per, (rank + 1) * per) == 0
+    t_part = time.time() - t_setup
+    assert capi.lib.preAlps_b200_BlockJacobiCreate() == 0
+    t_setup = time.time() - t_setup
+    arr_m = C.c_int(); arr_M = C.c_int()
+    capi.lib.preAlps_OperatorGetSizes(C.byref(arr_M), C.byref(arr_m))
+    m = arr_m.value
+    rhs = capi.driver_rhs(m)
+
+    # ---- e2e: whole solves through the RCI API with host buffers (the first one also warms everything up)
+    barrier()
+    sol, hist, info0 = capi.solve(rhs, args.t, args.tol)
+    barrier()
+    sol, hist, info = capi.solve(rhs, args.t, args.tol)
+    barrier()
+    tts = max_over_ranks(info.t_solve)
+    e2e_value = info.iter / tts
+
+    # ---- timed region: exactly K iterations, device resident, CUDA events, max over ranks
+    ms = C.c_float()
+    launches = C.c_longlong()
+    barrier()
+    with ClockSampler(local) as clk:
+        assert capi.lib.preAlps_b200_BenchIterations(args.t, C.c_double(args.tol), 0, capi.dp(rhs), args.warmup, args.steps,
+                                                     C.byref(ms), C.byref(launches)) == 0
+        barrier()
+    ms_total = max_over_ranks(float(ms.value))
+    value = args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel roofline, timed alone with an L2 flush between repetitions
+    peak, peak_kind = measured_peaks()
+    kern = {}
+    for what, name, bytes_name in ((1, "block_jacobi_apply", "bj_bytes_t%d" % args.t), (0, "spmm", "spmm_bytes_t%d" % args.t),
+                                   (2, "ecg_dense_passes", None)):
+        kms = C.c_float()
+        assert capi.lib.preAlps_b200_BenchKernel(what, args.t, 10, 1, C.byref(kms)) == 0
+        kt = max_over_ranks(float(kms.value))
+        if bytes_name:
+            b = capi.stat(bytes_name)
+        else:
+            b = 18.0 * m * args.t * 8.0  # fused dense traffic, 18 block passes per iteration
+        kern[name] = {"ms": kt, "algorithmic_bytes": b, "achieved_gbs": b / (kt * 1e-3) / 1e9,
+                      "frac_of_%s_peak" % peak_kind: b / (kt * 1e-3) / 1e9 / peak}
+    bj = kern["block_jacobi_apply"]
+    roofline = {"bound": "hbm", "kernel": "bj sweep_kernel<8> (forward + backward levels of one block-Jacobi apply)",
+                "achieved": bj["achieved_gbs"], "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
+                "frac": bj["achieved_gbs"] / peak, "traffic": None,
+                "frac_of_nominal_8TBs": bj["achieved_gbs"] / 8000.0}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = reference_arm(args, as_baseline=True)
+            except Exception as e:  # the baseline must never take the GPU line down
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int((m * 8 + m * 4) / max(info.iter, 1)),
+                    "d2h_bytes_per_step": int(m * 8 / max(info.iter, 1) + 8),
+                    "time_to_solution_s": tts, "iterations": info.iter, "final_res": info.res,
+                    "true_relres": info.true_relres, "device_ms": info.t_dev_ms},
+            "gpu_launches": int(launches.value),
+            "clocks": clk.summary(),
+            "roofline": roofline,
+            "kernels": kern,
+            "cpu_baseline": cpu,
+            "setup": {"partition_s": t_part, "total_s": t_setup, "bj_analysis_s": capi.stat("bj_analysis_s"),
+                      "bj_factor_s": capi.stat("bj_factor_s"), "bj_nnz_exact": capi.stat("bj_nnz_exact"),
+                      "bj_nnz_stored": capi.stat("bj_nnz_stored"), "bj_supernodes": capi.stat("bj_supernodes"),
+                      "bj_levels": capi.stat("bj_levels"), "rows_per_gpu": m},
+        }
+        print(json.dumps(line))
+    barrier()
+    capi.lib.preAlps_OperatorFree()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
