@@ -65,6 +65,7 @@ struct pcu_bj {
   pcu::WorkUnit* fwd_units = nullptr;
   pcu::WorkUnit* bwd_units = nullptr;
   std::vector<int> fwd_unit_ptr, bwd_unit_ptr;   // per level, nlevels+1
+  std::vector<double> fwd_lvl_bytes, bwd_lvl_bytes;  // panel bytes per level (profiling)
   // device: assembly of the forward right-hand side
   int* perm = nullptr;             // perm[forest col] = local row of the m x t block
   int* rows = nullptr;             // forest row index of every supernode row (gather index of the backward sweep)

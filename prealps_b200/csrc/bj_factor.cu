@@ -525,6 +525,8 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   std::vector<BwdPanel> bp;
   std::vector<WorkUnit> fu, bu;
   bj->fwd_unit_ptr.assign(nlev + 1, 0);
+  bj->fwd_lvl_bytes.assign(nlev, 0.0);
+  bj->bwd_lvl_bytes.assign(nlev, 0.0);
   bj->bwd_unit_ptr.assign(nlev + 1, 0);
   std::vector<std::vector<PackTask>> pk_f(nlev), pk_b(nlev);
   long long fdoubles = 0, bdoubles = 0;
@@ -554,6 +556,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       FwdPanel P{fdoubles, uoff[s], e.first, sn_c0[s], 32 * p, sn_w[s], sn_h[s], 0};
       pk_f[l].push_back({zoff[s], fdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
       fdoubles += (long long)e.first * 32;
+      bj->fwd_lvl_bytes[l] += 8.0 * e.first * 32;
       fp.push_back(P);
     }
     kl.resize(fp.size());
@@ -577,6 +580,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       BwdPanel P{bdoubles, sn_rp[s], e.first, 32 * p, sn_c0[s], sn_w[s], sn_h[s], 0};
       pk_b[l].push_back({zoff[s], bdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
       bdoubles += (long long)e.first * 32;
+      bj->bwd_lvl_bytes[l] += 8.0 * e.first * 32;
       bp.push_back(P);
     }
     kl.assign(bp.size(), 0);

@@ -14,6 +14,7 @@
 // panels get a whole CTA (split-K over 8 warps, fixed-order combine in shared memory).
 // No atomics: results are bit-reproducible.
 #include <algorithm>
+#include <string>
 
 #include "bj.h"
 
@@ -68,12 +69,40 @@ struct SweepArgs {
   double* Out; int ldo; int t;
 };
 
-template <int T, bool FWD>
-__global__ void __launch_bounds__(kThreads) sweep_kernel(SweepArgs a) {
-  __shared__ double red[32 * T];
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// rows of the input block staged per tile and per warp (4 KB per buffer at any T)
+template <int T>
+struct Tile { static constexpr int KT = (T <= 8) ? 64 : (512 / T); };  // k steps per tile, even, KT*T*8 = 4 KB for T >= 8
+
+
+// One warp per short panel, or the 8 warps of a CTA on disjoint k ranges of one long panel.
+// Per warp: (1) a ring of D panel loads (16 B per lane each, HBM latency) is always in flight,
+// (2) the T-wide input rows of the next 64 k steps are copied into a warp-private shared-memory tile
+// with cp.async (LDGSTS, no registers) while the current tile is consumed, so the FMAs only ever
+// wait on shared-memory broadcasts.  Measured before this pipeline: long-scoreboard bound, 2.1 TB/s.
+template <int T, bool FWD, int D, bool NOALLOC>
+__global__ void __launch_bounds__(kThreads, 2) sweep_kernel(SweepArgs a) {
+  constexpr int KT = Tile<T>::KT;       // k steps per tile
+  constexpr int KP = KT / 2;            // k pairs per tile
+  constexpr int TILE = KT * T;          // doubles per tile buffer
+  extern __shared__ __align__(16) double smem[];
+  double* red = smem;                   // 32 * T doubles
   const WorkUnit u = a.units[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, j = lane & 15;
+  double* tile0 = smem + 32 * T + (size_t)warp * 2 * TILE;
   if (!u.split && warp >= u.count) return;
   const int pidx = u.split ? u.first : u.first + warp;
   long long off;
@@ -86,43 +115,90 @@ __global__ void __launch_bounds__(kThreads) sweep_kernel(SweepArgs a) {
     const BwdPanel p = reinterpret_cast<const BwdPanel*>(a.panels)[pidx];
     off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
   }
-  // k range of this warp, in pairs of k (each half-warp takes one k of the pair)
   const int npair = klen >> 1;
   int p0 = 0, p1 = npair;
   if (u.split) {
-    const int per = (npair + kWarps - 1) / kWarps;
+    int per = (npair + kWarps - 1) / kWarps;
+    per = (per + KP - 1) / KP * KP;     // whole tiles per warp
     p0 = min(npair, warp * per);
     p1 = min(npair, p0 + per);
   }
   double acc0[T], acc1[T];
 #pragma unroll
   for (int c = 0; c < T; ++c) { acc0[c] = 0.0; acc1[c] = 0.0; }
-  const double* base = a.data + off + 2 * j;
+  const double* base = a.data + off + 2 * j + (size_t)half * 32;
   const int* rows = a.rows + rows_off;
-#pragma unroll 4
-  for (int kp = p0; kp < p1; ++kp) {
-    const int k = 2 * kp + half;
-    const double2 m = __ldg(reinterpret_cast<const double2*>(base + (size_t)k * 32));
-    const double* bp;
-    if (FWD) {
-      bp = a.Wk + (size_t)(c0 + k) * T;
-    } else {
-      const int i = min(row0 + k, h - 1);
-      bp = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
-    }
-    if (T >= 2) {
+
+  // copy the input rows of k in [2*tp, 2*tp + KT) into buf (rows past the panel are clamped: their
+  // panel entries are zero padding)
+  auto stage = [&](int tp, double* buf) {
+    constexpr int CHUNKS = (T >= 2) ? TILE / 2 : KT;  // 16-byte pieces per tile (rows when T == 1)
+    constexpr int CPR = (T >= 2) ? T / 2 : 1; // pieces per row
 #pragma unroll
-      for (int c = 0; c < T; c += 2) {
-        const double2 b = *reinterpret_cast<const double2*>(bp + c);
-        acc0[c] = fma(m.x, b.x, acc0[c]);
-        acc1[c] = fma(m.y, b.x, acc1[c]);
-        acc0[c + 1] = fma(m.x, b.y, acc0[c + 1]);
-        acc1[c + 1] = fma(m.y, b.y, acc1[c + 1]);
+    for (int q0 = 0; q0 < CHUNKS; q0 += 32) {
+      const int q = q0 + lane;
+      if (T >= 2) {
+        const int r = q / CPR, part = q % CPR;
+        const int k = min(2 * tp + r, klen - 1);
+        const double* src;
+        if (FWD) src = a.Wk + (size_t)(c0 + k) * T;
+        else {
+          const int i = min(row0 + k, h - 1);
+          src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
+        }
+        cp_async16(buf + (size_t)r * T + 2 * part, src + 2 * part);
+      } else {  // T == 1: two rows per 16-byte piece do not share a source row; plain loads
+        const int k = min(2 * tp + q, klen - 1);
+        if (q < KT) {
+          const double* src;
+          if (FWD) src = a.Wk + (size_t)(c0 + k);
+          else { const int i = min(row0 + k, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
+          buf[q] = *src;
+        }
       }
-    } else {
-      const double b = bp[0];
-      acc0[0] = fma(m.x, b, acc0[0]);
-      acc1[0] = fma(m.y, b, acc1[0]);
+    }
+    cp_async_commit();
+  };
+
+  double2 ring[D];
+  auto issue = [&](int kp, double2& m) {
+    if (kp < p1) m = NOALLOC ? ld_stream2(base + (size_t)kp * 64) : __ldg(reinterpret_cast<const double2*>(base + (size_t)kp * 64));
+    else m = make_double2(0.0, 0.0);
+  };
+  if (p0 < p1) {
+    stage(p0, tile0);
+#pragma unroll
+    for (int u2 = 0; u2 < D; ++u2) issue(p0 + u2, ring[u2]);
+    int tix = 0;
+    for (int tp = p0; tp < p1; tp += KP, ++tix) {
+      double* cur = tile0 + (size_t)(tix & 1) * TILE;
+      if (tp + KP < p1) { stage(tp + KP, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncwarp();
+#pragma unroll 1
+      for (int kq = 0; kq < KP; kq += D) {
+#pragma unroll
+        for (int u2 = 0; u2 < D; ++u2) {
+          const double2 m = ring[u2];
+          issue(tp + kq + u2 + D, ring[u2]);
+          const double* bp = cur + (size_t)(2 * (kq + u2) + half) * T;
+          if (T >= 2) {
+#pragma unroll
+            for (int c = 0; c < T; c += 2) {
+              const double2 bb = *reinterpret_cast<const double2*>(bp + c);
+              acc0[c] = fma(m.x, bb.x, acc0[c]);
+              acc1[c] = fma(m.y, bb.x, acc1[c]);
+              acc0[c + 1] = fma(m.x, bb.y, acc0[c + 1]);
+              acc1[c + 1] = fma(m.y, bb.y, acc1[c + 1]);
+            }
+          } else {
+            const double bb = bp[0];
+            acc0[0] = fma(m.x, bb, acc0[0]);
+            acc1[0] = fma(m.y, bb, acc1[0]);
+          }
+        }
+      }
+      __syncwarp();
     }
   }
   // combine the two half-warps (even k + odd k); afterwards lane (half, j) owns row 2j + half
@@ -177,7 +253,7 @@ int ensure_work(pcu_bj* bj, int T) {
   PCU_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp);
   bj->Wk = bj->Y = bj->U = bj->Xp = nullptr;
-  const size_t nv = ((size_t)bj->n + 4) * T, nuv = ((size_t)bj->nu + 4) * T;
+  const size_t nv = ((size_t)bj->n + 72) * T, nuv = ((size_t)bj->nu + 4) * T;
   PCU_CUDA(cudaMalloc(&bj->Wk, nv * sizeof(double)));
   PCU_CUDA(cudaMalloc(&bj->Y, nv * sizeof(double)));
   PCU_CUDA(cudaMalloc(&bj->Xp, nv * sizeof(double)));
@@ -190,10 +266,63 @@ int ensure_work(pcu_bj* bj, int T) {
   return 0;
 }
 
+template <int T, bool FWD, int D, bool NOALLOC>
+void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
+  constexpr int bytes = (32 * T + kWarps * 2 * Tile<T>::KT * T) * (int)sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(sweep_kernel<T, FWD, D, NOALLOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    configured = true;
+  }
+  sweep_kernel<T, FWD, D, NOALLOC><<<nu, kThreads, bytes, st>>>(a);
+}
+
+template <int T, bool FWD>
+void launch_sweep(int nu, cudaStream_t st, const SweepArgs& a) {
+  const char* e = getenv("PREALPS_BJ_VARIANT");
+  const int variant = e ? atoi(e) : 0;
+  switch (variant) {
+    case 1: launch_one<T, FWD, 4, true>(nu, st, a); break;
+    case 2: launch_one<T, FWD, 8, false>(nu, st, a); break;
+    case 3: launch_one<T, FWD, 4, false>(nu, st, a); break;
+    default: launch_one<T, FWD, 8, true>(nu, st, a); break;
+  }
+}
+
+// PREALPS_BJ_PROFILE=1: per-launch CUDA-event timings of one apply, printed to stderr
+struct LevelProfiler {
+  bool on = false;
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> tag;
+  std::vector<double> bytes;
+  explicit LevelProfiler(cudaStream_t s) : st(s) { on = getenv("PREALPS_BJ_PROFILE") != nullptr; }
+  void mark(const std::string& name, double b) {
+    if (!on) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+    ev.push_back(e); tag.push_back(name); bytes.push_back(b);
+  }
+  void report() {
+    if (!on || ev.empty()) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); cudaEventSynchronize(e);
+    ev.push_back(e);
+    double tot = 0, totb = 0;
+    for (size_t i = 0; i + 1 < ev.size(); ++i) {
+      float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      fprintf(stderr, "  %-22s %9.1f us %10.1f MB %8.1f GB/s\n", tag[i].c_str(), ms * 1e3, bytes[i] / 1e6,
+              bytes[i] / (ms * 1e-3) / 1e9);
+      tot += ms; totb += bytes[i];
+    }
+    fprintf(stderr, "  total %.3f ms, %.1f MB, %.1f GB/s\n", tot, totb / 1e6, totb / (tot * 1e-3) / 1e9);
+    for (auto x : ev) cudaEventDestroy(x);
+  }
+};
+
 template <int T>
 int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   pcu_ctx* c = bj->ctx;
   cudaStream_t st = c->stream;
+  LevelProfiler prof(st);
   constexpr int G = (T >= 2) ? T / 2 : 1;
   SweepArgs a{};
   a.Wk = bj->Wk; a.Y = bj->Y; a.U = bj->U; a.Xp = bj->Xp; a.rows = bj->rows; a.perm = bj->perm;
@@ -201,6 +330,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   for (int l = 0; l < bj->nlevels; ++l) {
     const int ncols = bj->lvl_col_ptr[l + 1] - bj->lvl_col_ptr[l];
     if (ncols > 0) {
+      prof.mark("asm L" + std::to_string(l) + " cols=" + std::to_string(ncols), 3.0 * ncols * T * 8);
       const int grid = stream_grid(c, (long long)ncols * G, kThreads, 8);
       assemble_kernel<T><<<grid, kThreads, 0, st>>>(bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t, bj->perm,
                                                    bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
@@ -208,23 +338,26 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
     }
     const int nu = bj->fwd_unit_ptr[l + 1] - bj->fwd_unit_ptr[l];
     if (nu > 0) {
+      prof.mark("fwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->fwd_lvl_bytes[l]);
       a.units = bj->fwd_units + bj->fwd_unit_ptr[l];
       a.panels = bj->fwd_panels;
       a.data = bj->fwd_data;
-      sweep_kernel<T, true><<<nu, kThreads, 0, st>>>(a);
+      launch_sweep<T, true>(nu, st, a);
       PCU_LAUNCH_CHECK(c);
     }
   }
   for (int l = bj->nlevels - 1; l >= 0; --l) {
     const int nu = bj->bwd_unit_ptr[l + 1] - bj->bwd_unit_ptr[l];
     if (nu > 0) {
+      prof.mark("bwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->bwd_lvl_bytes[l]);
       a.units = bj->bwd_units + bj->bwd_unit_ptr[l];
       a.panels = bj->bwd_panels;
       a.data = bj->bwd_data;
-      sweep_kernel<T, false><<<nu, kThreads, 0, st>>>(a);
+      launch_sweep<T, false>(nu, st, a);
       PCU_LAUNCH_CHECK(c);
     }
   }
+  prof.report();
   return 0;
 }
 

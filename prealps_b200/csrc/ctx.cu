@@ -110,6 +110,12 @@ int pcu_ctx_create(int device, pcu_ctx** out) {
   PCU_CUDA(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   PCU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    PCU_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    PCU_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   for (int i = 0; i < 16; ++i) {
     PCU_CUDA(cudaEventCreate(&c->ev_start[i]));
     PCU_CUDA(cudaEventCreate(&c->ev_stop[i]));
@@ -137,17 +143,19 @@ int pcu_sync(pcu_ctx* c) {
   return 0;
 }
 
+// Stream-ordered allocations from the device's default pool, which is told to keep freed memory:
+// a solver that is created and destroyed per solve (ECGInitialize .. ECGFinalize) then never pays
+// for cudaMalloc/cudaFree again (measured: 0.17 s + 0.16 s per solve at 64^3 with the plain calls).
 void* pcu_malloc(pcu_ctx* c, size_t bytes) {
   void* p = nullptr;
   cudaSetDevice(c->device);
-  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+  cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, c->stream);
   if (e != cudaSuccess) { set_error("pcu_malloc(%zu): %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
   return p;
 }
 int pcu_free(pcu_ctx* c, void* p) {
   if (!p) return 0;
-  PCU_CUDA(cudaStreamSynchronize(c->stream));
-  PCU_CUDA(cudaFree(p));
+  PCU_CUDA(cudaFreeAsync(p, c->stream));
   return 0;
 }
 int pcu_memset(pcu_ctx* c, void* p, int byte, size_t bytes) {

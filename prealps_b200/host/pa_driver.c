@@ -70,6 +70,7 @@ int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int b
   const double t0 = pa_wtime();
   pcu_timer_start(c, 0);
   preAlps_ECGInitialize(&ecg, rhs, &rci);
+  const double t_init = pa_wtime();
   preAlps_BlockJacobiApply(ecg.R, ecg.P);
   preAlps_BlockOperator(ecg.P, ecg.AP);
   while (stop != 1) {
@@ -87,9 +88,13 @@ int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int b
   }
   const int iter = ecg.iter;
   const double res = ecg.res, normb = ecg.normb;
+  const double t_loop = pa_wtime();
   preAlps_ECGFinalize(&ecg, sol);
   pcu_timer_stop(c, 0);
   const double t1 = pa_wtime();
+  if (getenv("PREALPS_B200_TIMING"))
+    fprintf(stderr, "[prealps_b200] solve: init %.4f s, loop %.4f s (%d iterations), finalize %.4f s\n", t_init - t0,
+            t_loop - t_init, iter, t1 - t_loop);
   float ms = 0.f;
   pcu_timer_elapsed_ms(c, 0, &ms);
   if (info) {

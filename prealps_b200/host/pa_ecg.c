@@ -128,7 +128,7 @@ int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
     const int r0 = g->built ? g->rowPos[g->s_lo + s] - g->g0 : 0;
     const int r1 = g->built ? g->rowPos[g->s_lo + s + 1] - g->g0 : m;
     double part = 0.0;
-    for (int i = r0; i < r1; ++i) part += pow(rhs[i], 2);
+    for (int i = r0; i < r1; ++i) part += rhs[i] * rhs[i];  /* == pow(x, 2) bit for bit */
     nb += part;
     /* R0 = T(b): the rows of subdomain s feed column s % t (ref: ecg.c:162 with rank -> subdomain id) */
     const int col = ((g->built ? g->s_lo : g->rank) + s) % t;
