@@ -132,8 +132,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=128, help="grid points per dimension")
-    ap.add_argument("--t", type=int, default=8, help="enlarging factor")
+    ap.add_argument("--grid", dest="n", type=int, default=128, help="grid points per dimension")
+    ap.add_argument("--enl", dest="t", type=int, default=8, help="enlarging factor t")
     ap.add_argument("--nsub", type=int, default=8, help="METIS subdomains = block-Jacobi blocks")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--ref-n", type=int, default=64, help="grid size of the CPU sample")

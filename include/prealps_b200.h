@@ -45,6 +45,8 @@ int preAlps_b200_GetPartition(int* S, int* s_lo, int* s_hi);
 int preAlps_b200_GetPerm(int** perm, int* n);                 /* perm[new] = old; rank that built it only */
 int preAlps_b200_GetDiagBlock(int b, CPLM_Mat_CSR_t* D);       /* b-th local block, upper triangle */
 int preAlps_b200_GetHalo(int** halo_cols, int* nhalo);        /* sorted global columns read from other processes */
+/* halo plan at process granularity: neighbours (ascending), local rows sent to each, slices of the halo received */
+int preAlps_b200_GetHaloPlan(int* nnbr, int** nbr, int** send_ptr, int** send_idx, int** recv_ptr);
 double preAlps_b200_Stat(const char* name);                   /* "spmm_bytes_t8", "bj_bytes_t8", "bj_nnz_exact", ... */
 
 /* ---- the driver's right-hand side, per subdomain: srand(0); rhs[i] = rand()/RAND_MAX;

@@ -134,9 +134,13 @@ static int finish_build(void) {
     CPLM_Abort("There is no dependencies between some blocks of A...");  /* ref: cplm_v0_matcsr.c:263 */
   int* colLoc = NULL;
   pa_halo_map(&g->A, g->g0, g->g1, &g->halo, &g->nhalo, &colLoc);
-  pcu_ctx* c = pa_ctx();
-  pa_cuda_check(pcu_spmm_create(c, g->m, g->nhalo, g->A.rowPtr, colLoc, g->A.val, &g->spmm), "pcu_spmm_create");
+  /* PREALPS_B200_HOST_ONLY=1: stop before anything touches the device (CPU tests of the partition / halo plan) */
+  const int host_only = getenv("PREALPS_B200_HOST_ONLY") != NULL;
+  pcu_ctx* c = host_only ? NULL : pa_ctx();
+  if (!host_only)
+    pa_cuda_check(pcu_spmm_create(c, g->m, g->nhalo, g->A.rowPtr, colLoc, g->A.val, &g->spmm), "pcu_spmm_create");
   free(colLoc);
+  if (host_only && g->xport == PA_XPORT_NCCL) CPLM_Abort("host-only mode needs the MPI transport");
   if (g->nproc > 1) {
     /* who needs how many rows from whom: need[p*nproc + q] = rows p reads from q */
     const int np = g->nproc;
@@ -187,7 +191,8 @@ static int finish_build(void) {
       g->send_idx[i] -= g->g0;  /* global -> local row */
       if (g->send_idx[i] < 0 || g->send_idx[i] >= g->m) CPLM_Abort("halo plan: neighbour asked for a row I do not own");
     }
-    pa_cuda_check(pcu_spmm_set_halo(g->spmm, g->nnbr, g->nbr, g->send_ptr, g->send_idx, g->recv_ptr), "pcu_spmm_set_halo");
+    if (!host_only)
+      pa_cuda_check(pcu_spmm_set_halo(g->spmm, g->nnbr, g->nbr, g->send_ptr, g->send_idx, g->recv_ptr), "pcu_spmm_set_halo");
     free(mine); free(need);
   } else if (g->nhalo > 0) {
     CPLM_Abort("single process but %d columns fall outside its rows", g->nhalo);
@@ -432,6 +437,10 @@ int preAlps_OperatorGetDepPtr(int** dep, int* n) { *n = pa_g.ndep; *dep = pa_g.d
 int preAlps_b200_GetPartition(int* S, int* s_lo, int* s_hi) { *S = pa_g.S; *s_lo = pa_g.s_lo; *s_hi = pa_g.s_hi; return 0; }
 int preAlps_b200_GetPerm(int** perm, int* n) { *perm = pa_g.perm; *n = pa_g.nperm; return pa_g.perm == NULL; }
 int preAlps_b200_GetHalo(int** halo, int* n) { *halo = pa_g.halo; *n = pa_g.nhalo; return 0; }
+int preAlps_b200_GetHaloPlan(int* nnbr, int** nbr, int** send_ptr, int** send_idx, int** recv_ptr) {
+  *nnbr = pa_g.nnbr; *nbr = pa_g.nbr; *send_ptr = pa_g.send_ptr; *send_idx = pa_g.send_idx; *recv_ptr = pa_g.recv_ptr;
+  return 0;
+}
 
 void preAlps_OperatorPrint(int rank) {
   if (rank != 0) return;
