@@ -153,6 +153,13 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # exactly ONE JSON line may reach stdout: send everything libraries print (NCCL's version banner, ...)
+    # to stderr and keep the real stdout for the result
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+
     import ctypes as C
     import numpy as np
     import torch
@@ -268,7 +275,7 @@ def main():
                       "bj_nnz_stored": capi.stat("bj_nnz_stored"), "bj_supernodes": capi.stat("bj_supernodes"),
                       "bj_levels": capi.stat("bj_levels"), "rows_per_gpu": m},
         }
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     barrier()
     capi.lib.preAlps_OperatorFree()
     if dist is not None:
