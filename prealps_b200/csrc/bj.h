@@ -7,11 +7,13 @@
 //   streaming products without any intra-supernode dependency:
 //     forward   [y_s ; u_s] = M_s b_s          (u_s = contribution to the ancestors)
 //     backward  x_s = M_s^T [y_s ; -x_below]
-//   M_s is stored twice, cut into 32-row panels, each panel "k-major":
-//     fwd panel p of s: rows [32p, 32p+32) of M_s,   data[k*32 + r] = M_s(32p + r, k),  k < klen
-//     bwd panel q of s: rows [32q, 32q+32) of M_s^T, data[k*32 + r] = +-M_s(32q + k', 32q + r)
-//   so a warp streams a panel with perfectly coalesced 512-byte loads while the t-wide
-//   input row needed for step k is the same for all lanes (broadcast load).
+//   M_s is stored twice, cut into 32-row panels of klen steps (klen a multiple of 4):
+//     fwd panel p of s: rows [32p, 32p+32) of M_s,   steps k = columns of M_s
+//     bwd panel q of s: rows [32q, 32q+32) of M_s^T, steps k = rows 32q.. of M_s (lower part negated)
+//   A panel is a sequence of k-blocks (4 steps, 128 doubles = 1 KB) stored in the A-fragment order of
+//   mma.sync.m8n8k4.f64: data[kb*128 + lane*4 + rg] = panel(8*rg + lane/4, 4*kb + lane%4).  A warp streams a
+//   panel with perfectly coalesced 1 KB reads (32 B per lane) and multiplies it with the t-wide input rows
+//   (B fragment: one shared-memory double per lane and k-block) on the FP64 tensor cores.
 #pragma once
 #include <cstdint>
 #include <vector>

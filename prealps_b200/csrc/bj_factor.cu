@@ -302,14 +302,17 @@ __global__ void minit_kernel(const SnDev* __restrict__ sns, const double* __rest
   }
 }
 
+// Panel layout (bj.h): k-blocks of 4 steps; inside a k-block the 128 values are stored in DMMA A-fragment
+// order, element e = lane*4 + rg holding M(row0 + 8*rg + lane/4, 4*kb + lane%4), so that a lane reads its four
+// row-group values of one k-block as 32 contiguous bytes and a warp reads 1 KB contiguous per k-block.
 __global__ void pack_fwd_kernel(const PackTask* __restrict__ tasks, const double* __restrict__ Mbuf, double* __restrict__ out) {
   const PackTask t = tasks[blockIdx.x];
   const double* M = Mbuf + t.moff;
   double* dst = out + t.dst;
   const long long tot = (long long)t.klen * 32;
   for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
-    const int r = (int)(e % 32), k = (int)(e / 32);
-    const int i = t.row0 + r;
+    const int kb = (int)(e / 128), rem = (int)(e % 128), lane = rem / 4, rg = rem % 4;
+    const int i = t.row0 + 8 * rg + lane / 4, k = 4 * kb + lane % 4;
     double v = 0.0;
     if (i < t.h && k < t.w && (i >= t.w || k <= i)) v = M[i + (long long)k * t.h];
     dst[e] = v;
@@ -321,10 +324,10 @@ __global__ void pack_bwd_kernel(const PackTask* __restrict__ tasks, const double
   const double* M = Mbuf + t.moff;
   double* dst = out + t.dst;
   const long long tot = (long long)t.klen * 32;
-  // element (k, r): supernode row i = row0 + k, column c = row0 + r ; value M(i, c), negated for i >= w
+  // output row (a column c of the supernode) = row0 + 8*rg + lane/4 ; step k <-> supernode row i = row0 + 4*kb + lane%4
   for (long long e = threadIdx.x; e < tot; e += blockDim.x) {
-    const int r = (int)(e % 32), k = (int)(e / 32);
-    const int i = t.row0 + k, c = t.row0 + r;
+    const int kb = (int)(e / 128), rem = (int)(e % 128), lane = rem / 4, rg = rem % 4;
+    const int c = t.row0 + 8 * rg + lane / 4, i = t.row0 + 4 * kb + lane % 4;
     double v = 0.0;
     if (i < t.h && c < t.w && i >= c) { v = M[i + (long long)c * t.h]; if (i >= t.w) v = -v; }
     dst[e] = v;
@@ -544,7 +547,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       const int s = order[q];
       for (int p = 0; p * 32 < sn_h[s]; ++p) {
         int klen = std::min(sn_w[s], 32 * p + 32);
-        klen += klen & 1;
+        klen = (klen + 3) & ~3;  // whole k-blocks of 4 (one DMMA step)
         lst.push_back({klen, {s, p}});
       }
     }
@@ -569,7 +572,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       const int s = order[q];
       for (int p = 0; p * 32 < sn_w[s]; ++p) {
         int klen = sn_h[s] - 32 * p;
-        klen += klen & 1;
+        klen = (klen + 3) & ~3;  // whole k-blocks of 4 (one DMMA step)
         lst.push_back({klen, {s, p}});
       }
     }

@@ -87,21 +87,33 @@ template <int T>
 struct Tile { static constexpr int KT = (T <= 8) ? 64 : (512 / T); };  // k steps per tile, even, KT*T*8 = 4 KB for T >= 8
 
 
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // One warp per short panel, or the 8 warps of a CTA on disjoint k ranges of one long panel.
-// Per warp: (1) a ring of D panel loads (16 B per lane each, HBM latency) is always in flight,
-// (2) the T-wide input rows of the next 64 k steps are copied into a warp-private shared-memory tile
-// with cp.async (LDGSTS, no registers) while the current tile is consumed, so the FMAs only ever
-// wait on shared-memory broadcasts.  Measured before this pipeline: long-scoreboard bound, 2.1 TB/s.
-template <int T, bool FWD, int D, bool NOALLOC>
-__global__ void __launch_bounds__(kThreads, 2) sweep_kernel(SweepArgs a) {
-  constexpr int KT = Tile<T>::KT;       // k steps per tile
-  constexpr int KP = KT / 2;            // k pairs per tile
+// Per warp and k-block (4 steps): 1 KB of the panel (32 B per lane, already in A-fragment order), one
+// shared-memory double per lane (B fragment of the T-wide input rows) and 4 DMMA per 8 output columns.
+//   (1) a ring of D k-blocks of panel data is always in flight (HBM latency),
+//   (2) the input rows of the next tile of k steps are copied into a warp-private shared-memory buffer with
+//       cp.async while the current tile is consumed,
+//   (3) the accumulators are 2 doubles per 8x8 block (8 doubles at T = 8), which keeps the register budget for
+//       the ring: 3 CTAs/SM = 24 warps x 4 KB in flight.
+// History (128^3, t=8, whole apply): plain FMA loop 2.1 TB/s (long-scoreboard bound), + register ring 2.6,
+// + cp.async tiles 3.5, DMMA + fragment-order panels: see profiles/.
+template <int T, bool FWD, int D, bool NOALLOC, int OCC>
+__global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(SweepArgs a) {
+  constexpr int NB = (T + 7) / 8;       // 8-column blocks of the output
+  constexpr int KT = Tile<T>::KT;       // k steps per input tile
+  constexpr int KB = KT / 4;            // k-blocks per tile
   constexpr int TILE = KT * T;          // doubles per tile buffer
+  static_assert(KB % D == 0, "ring depth must divide the k-blocks of a tile");
   extern __shared__ __align__(16) double smem[];
   double* red = smem;                   // 32 * T doubles
   const WorkUnit u = a.units[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane >> 4, j = lane & 15;
+  const int lr = lane >> 2, lk = lane & 3;   // fragment row / k (or column pair)
   double* tile0 = smem + 32 * T + (size_t)warp * 2 * TILE;
   if (!u.split && warp >= u.count) return;
   const int pidx = u.split ? u.first : u.first + warp;
@@ -115,31 +127,33 @@ __global__ void __launch_bounds__(kThreads, 2) sweep_kernel(SweepArgs a) {
     const BwdPanel p = reinterpret_cast<const BwdPanel*>(a.panels)[pidx];
     off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
   }
-  const int npair = klen >> 1;
-  int p0 = 0, p1 = npair;
+  const int nkb = klen >> 2;
+  int q0 = 0, q1 = nkb;
   if (u.split) {
-    int per = (npair + kWarps - 1) / kWarps;
-    per = (per + KP - 1) / KP * KP;     // whole tiles per warp
-    p0 = min(npair, warp * per);
-    p1 = min(npair, p0 + per);
+    int per = (nkb + kWarps - 1) / kWarps;
+    per = (per + KB - 1) / KB * KB;     // whole tiles per warp
+    q0 = min(nkb, warp * per);
+    q1 = min(nkb, q0 + per);
   }
-  double acc0[T], acc1[T];
+  double acc[4][NB][2];
 #pragma unroll
-  for (int c = 0; c < T; ++c) { acc0[c] = 0.0; acc1[c] = 0.0; }
-  const double* base = a.data + off + 2 * j + (size_t)half * 32;
+  for (int rg = 0; rg < 4; ++rg)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
+  const double* base = a.data + off + lane * 4;
   const int* rows = a.rows + rows_off;
 
-  // copy the input rows of k in [2*tp, 2*tp + KT) into buf (rows past the panel are clamped: their
+  // copy the input rows of steps [4*tq, 4*tq + KT) into buf (steps past the panel are clamped: their
   // panel entries are zero padding)
-  auto stage = [&](int tp, double* buf) {
+  auto stage = [&](int tq, double* buf) {
     constexpr int CHUNKS = (T >= 2) ? TILE / 2 : KT;  // 16-byte pieces per tile (rows when T == 1)
-    constexpr int CPR = (T >= 2) ? T / 2 : 1; // pieces per row
+    constexpr int CPR = (T >= 2) ? T / 2 : 1;         // pieces per row
 #pragma unroll
-    for (int q0 = 0; q0 < CHUNKS; q0 += 32) {
-      const int q = q0 + lane;
+    for (int c0q = 0; c0q < CHUNKS; c0q += 32) {
+      const int q = c0q + lane;
       if (T >= 2) {
         const int r = q / CPR, part = q % CPR;
-        const int k = min(2 * tp + r, klen - 1);
+        const int k = min(4 * tq + r, klen - 1);
         const double* src;
         if (FWD) src = a.Wk + (size_t)(c0 + k) * T;
         else {
@@ -147,100 +161,115 @@ __global__ void __launch_bounds__(kThreads, 2) sweep_kernel(SweepArgs a) {
           src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
         }
         cp_async16(buf + (size_t)r * T + 2 * part, src + 2 * part);
-      } else {  // T == 1: two rows per 16-byte piece do not share a source row; plain loads
-        const int k = min(2 * tp + q, klen - 1);
-        if (q < KT) {
-          const double* src;
-          if (FWD) src = a.Wk + (size_t)(c0 + k);
-          else { const int i = min(row0 + k, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
-          buf[q] = *src;
-        }
+      } else if (q < KT) {
+        const int k = min(4 * tq + q, klen - 1);
+        const double* src;
+        if (FWD) src = a.Wk + (size_t)(c0 + k);
+        else { const int i = min(row0 + k, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
+        buf[q] = *src;
       }
     }
     cp_async_commit();
   };
 
-  double2 ring[D];
-  auto issue = [&](int kp, double2& m) {
-    if (kp < p1) m = NOALLOC ? ld_stream2(base + (size_t)kp * 64) : __ldg(reinterpret_cast<const double2*>(base + (size_t)kp * 64));
-    else m = make_double2(0.0, 0.0);
+  double2 ring0[D], ring1[D];
+  auto issue = [&](int kb, double2& m0, double2& m1) {
+    if (kb < q1) {
+      const double* p = base + (size_t)kb * 128;
+      if (NOALLOC) { m0 = ld_stream2(p); m1 = ld_stream2(p + 2); }
+      else { m0 = __ldg(reinterpret_cast<const double2*>(p)); m1 = __ldg(reinterpret_cast<const double2*>(p + 2)); }
+    } else {
+      m0 = make_double2(0.0, 0.0);
+      m1 = m0;
+    }
   };
-  if (p0 < p1) {
-    stage(p0, tile0);
+  if (q0 < q1) {
+    stage(q0, tile0);
 #pragma unroll
-    for (int u2 = 0; u2 < D; ++u2) issue(p0 + u2, ring[u2]);
+    for (int u2 = 0; u2 < D; ++u2) issue(q0 + u2, ring0[u2], ring1[u2]);
     int tix = 0;
-    for (int tp = p0; tp < p1; tp += KP, ++tix) {
-      double* cur = tile0 + (size_t)(tix & 1) * TILE;
-      if (tp + KP < p1) { stage(tp + KP, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
+    for (int tq = q0; tq < q1; tq += KB, ++tix) {
+      const double* cur = tile0 + (size_t)(tix & 1) * TILE;
+      if (tq + KB < q1) { stage(tq + KB, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
       else cp_async_wait<0>();
       __syncwarp();
 #pragma unroll 1
-      for (int kq = 0; kq < KP; kq += D) {
+      for (int kq = 0; kq < KB; kq += D) {
 #pragma unroll
         for (int u2 = 0; u2 < D; ++u2) {
-          const double2 m = ring[u2];
-          issue(tp + kq + u2 + D, ring[u2]);
-          const double* bp = cur + (size_t)(2 * (kq + u2) + half) * T;
-          if (T >= 2) {
+          const double2 m0 = ring0[u2], m1 = ring1[u2];
+          issue(tq + kq + u2 + D, ring0[u2], ring1[u2]);
+          const double* brow = cur + (size_t)(4 * (kq + u2) + lk) * T;
 #pragma unroll
-            for (int c = 0; c < T; c += 2) {
-              const double2 bb = *reinterpret_cast<const double2*>(bp + c);
-              acc0[c] = fma(m.x, bb.x, acc0[c]);
-              acc1[c] = fma(m.y, bb.x, acc1[c]);
-              acc0[c + 1] = fma(m.x, bb.y, acc0[c + 1]);
-              acc1[c + 1] = fma(m.y, bb.y, acc1[c + 1]);
-            }
-          } else {
-            const double bb = bp[0];
-            acc0[0] = fma(m.x, bb, acc0[0]);
-            acc1[0] = fma(m.y, bb, acc1[0]);
+          for (int nb = 0; nb < NB; ++nb) {
+            const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
+            dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
+            dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
+            dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
+            dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
           }
         }
       }
       __syncwarp();
     }
   }
-  // combine the two half-warps (even k + odd k); afterwards lane (half, j) owns row 2j + half
-  double mine[T];
-#pragma unroll
-  for (int c = 0; c < T; ++c) {
-    const double s0 = acc0[c] + __shfl_xor_sync(0xffffffffu, acc0[c], 16);
-    const double s1 = acc1[c] + __shfl_xor_sync(0xffffffffu, acc1[c], 16);
-    mine[c] = half ? s1 : s0;
-  }
-  const int rloc = 2 * j + half;
+  // lane owns, for every row group rg and column block nb: row 8*rg + lane/4, columns 8*nb + 2*(lane%4) + {0,1}
   if (u.split) {
-    // fixed-order combine over the warps
-    for (int wv = 0; wv < kWarps; ++wv) {
+    for (int wv = 0; wv < kWarps; ++wv) {  // fixed-order combine over the warps
       if (warp == wv) {
 #pragma unroll
-        for (int c = 0; c < T; ++c) {
-          if (wv == 0) red[rloc * T + c] = mine[c];
-          else red[rloc * T + c] += mine[c];
-        }
+        for (int rg = 0; rg < 4; ++rg)
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = 8 * nb + 2 * lk + e;
+              if (col < T) {
+                double* dst = red + (8 * rg + lr) * T + col;
+                if (wv == 0) *dst = acc[rg][nb][e]; else *dst += acc[rg][nb][e];
+              }
+            }
       }
       __syncthreads();
     }
     if (warp != 0) return;
 #pragma unroll
-    for (int c = 0; c < T; ++c) mine[c] = red[rloc * T + c];
+    for (int rg = 0; rg < 4; ++rg)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * nb + 2 * lk + e;
+          if (col < T) acc[rg][nb][e] = red[(8 * rg + lr) * T + col];
+        }
   }
-  const int r = row0 + rloc;
-  if (FWD) {
-    if (r < h) {
-      double* dst = (r < w) ? a.Y + (size_t)(c0 + r) * T : a.U + (size_t)(uoff + (r - w)) * T;
 #pragma unroll
-      for (int c = 0; c < T; ++c) dst[c] = mine[c];
+  for (int rg = 0; rg < 4; ++rg) {
+    const int r = row0 + 8 * rg + lr;
+    double* dst = nullptr;
+    double* out = nullptr;
+    if (FWD) {
+      if (r < h) dst = (r < w) ? a.Y + (size_t)(c0 + r) * T : a.U + (size_t)(uoff + (r - w)) * T;
+    } else if (r < w) {
+      dst = a.Xp + (size_t)(c0 + r) * T;
+      out = a.Out + (size_t)a.perm[c0 + r] * a.ldo;
     }
-  } else {
-    if (r < w) {
-      double* dst = a.Xp + (size_t)(c0 + r) * T;
+    if (!dst) continue;
 #pragma unroll
-      for (int c = 0; c < T; ++c) dst[c] = mine[c];
-      double* o = a.Out + (size_t)a.perm[c0 + r] * a.ldo;
-#pragma unroll
-      for (int c = 0; c < T; ++c) if (c < a.t) o[c] = mine[c];
+    for (int nb = 0; nb < NB; ++nb) {
+      const int col = 8 * nb + 2 * lk;
+      if (T >= 2) {
+        if (col < T) {
+          *reinterpret_cast<double2*>(dst + col) = make_double2(acc[rg][nb][0], acc[rg][nb][1]);
+          if (out) {
+            if (col < a.t) out[col] = acc[rg][nb][0];
+            if (col + 1 < a.t) out[col + 1] = acc[rg][nb][1];
+          }
+        }
+      } else if (col == 0) {
+        dst[0] = acc[rg][nb][0];
+        if (out) out[0] = acc[rg][nb][0];
+      }
     }
   }
 }
@@ -266,15 +295,15 @@ int ensure_work(pcu_bj* bj, int T) {
   return 0;
 }
 
-template <int T, bool FWD, int D, bool NOALLOC>
+template <int T, bool FWD, int D, bool NOALLOC, int OCC>
 void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
   constexpr int bytes = (32 * T + kWarps * 2 * Tile<T>::KT * T) * (int)sizeof(double);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_kernel<T, FWD, D, NOALLOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(sweep_kernel<T, FWD, D, NOALLOC, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     configured = true;
   }
-  sweep_kernel<T, FWD, D, NOALLOC><<<nu, kThreads, bytes, st>>>(a);
+  sweep_kernel<T, FWD, D, NOALLOC, OCC><<<nu, kThreads, bytes, st>>>(a);
 }
 
 template <int T, bool FWD>
@@ -282,10 +311,10 @@ void launch_sweep(int nu, cudaStream_t st, const SweepArgs& a) {
   const char* e = getenv("PREALPS_BJ_VARIANT");
   const int variant = e ? atoi(e) : 0;
   switch (variant) {
-    case 1: launch_one<T, FWD, 4, true>(nu, st, a); break;
-    case 2: launch_one<T, FWD, 8, false>(nu, st, a); break;
-    case 3: launch_one<T, FWD, 4, false>(nu, st, a); break;
-    default: launch_one<T, FWD, 8, true>(nu, st, a); break;
+    case 1: launch_one<T, FWD, (T <= 16 ? 8 : 4), true, 2>(nu, st, a); break;
+    case 2: launch_one<T, FWD, 4, false, 2>(nu, st, a); break;
+    case 3: launch_one<T, FWD, 2, true, 3>(nu, st, a); break;
+    default: launch_one<T, FWD, 4, true, 2>(nu, st, a); break;
   }
 }
 
