@@ -42,6 +42,9 @@ struct BwdPanel {      // one 32-row slice of M_s^T
   int pad_;
 };
 
+constexpr int kTinyS = 16;  // ... and the very short ones get a quarter of the buffer, 4x more warps per SM
+constexpr int kTinyK = 64;  // panels up to this many steps are staged whole into shared memory
+
 struct WorkUnit {      // one CTA of the sweep kernels
   int first;           // first panel
   int count;           // 1..8 panels (one per warp), or 1 panel split over all warps when split != 0
@@ -68,6 +71,9 @@ struct pcu_bj {
   pcu::WorkUnit* bwd_units = nullptr;
   std::vector<int> fwd_unit_ptr, bwd_unit_ptr;   // per level, nlevels+1
   std::vector<double> fwd_lvl_bytes, bwd_lvl_bytes;  // panel bytes per level (profiling)
+  // panels with klen <= kTinyK at the end of each level's (klen-descending) list go to the tiny-panel kernel
+  std::vector<int> fwd_tiny0, fwd_tinyn, bwd_tiny0, bwd_tinyn;
+  std::vector<int> fwd_tinys, bwd_tinys;  // of those, the last *_tinys panels have klen <= kTinyS
   // device: assembly of the forward right-hand side
   int* perm = nullptr;             // perm[forest col] = local row of the m x t block
   int* rows = nullptr;             // forest row index of every supernode row (gather index of the backward sweep)

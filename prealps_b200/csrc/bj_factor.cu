@@ -534,7 +534,19 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   std::vector<std::vector<PackTask>> pk_f(nlev), pk_b(nlev);
   long long fdoubles = 0, bdoubles = 0;
   const int kSplitK = 512;  // panels at least this long get a whole CTA (split-K over its 8 warps)
-  auto make_units = [&](std::vector<int>& klen_of, int first, int count, std::vector<WorkUnit>& units) {
+  bj->fwd_tiny0.assign(nlev, 0); bj->fwd_tinyn.assign(nlev, 0);
+  bj->bwd_tiny0.assign(nlev, 0); bj->bwd_tinyn.assign(nlev, 0);
+  bj->fwd_tinys.assign(nlev, 0); bj->bwd_tinys.assign(nlev, 0);
+  const bool use_tiny = getenv("PREALPS_BJ_NOTINY") == nullptr;
+  auto make_units = [&](std::vector<int>& klen_of, int first, int count_all, std::vector<WorkUnit>& units, int* tiny0,
+                        int* tinyn, int* tinys) {
+    int count = count_all;
+    if (use_tiny) while (count > 0 && klen_of[first + count - 1] <= kTinyK) --count;
+    *tiny0 = first + count;
+    *tinyn = count_all - count;
+    int cs = count_all;
+    while (cs > count && klen_of[first + cs - 1] <= kTinyS) --cs;
+    *tinys = count_all - cs;
     // panels [first, first+count) are already sorted by klen descending
     int i = 0;
     while (i < count && klen_of[first + i] >= kSplitK) { units.push_back({first + i, 1, 1, 0}); ++i; }
@@ -564,7 +576,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     }
     kl.resize(fp.size());
     for (size_t i = f0; i < fp.size(); ++i) kl[i] = fp[i].klen;
-    make_units(kl, f0, (int)fp.size() - f0, fu);
+    make_units(kl, f0, (int)fp.size() - f0, fu, &bj->fwd_tiny0[l], &bj->fwd_tinyn[l], &bj->fwd_tinys[l]);
     bj->fwd_unit_ptr[l + 1] = (int)fu.size();
     // backward
     lst.clear();
@@ -588,7 +600,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     }
     kl.assign(bp.size(), 0);
     for (size_t i = b0; i < bp.size(); ++i) kl[i] = bp[i].klen;
-    make_units(kl, b0, (int)bp.size() - b0, bu);
+    make_units(kl, b0, (int)bp.size() - b0, bu, &bj->bwd_tiny0[l], &bj->bwd_tinyn[l], &bj->bwd_tinys[l]);
     bj->bwd_unit_ptr[l + 1] = (int)bu.size();
   }
   bj->fwd_doubles = fdoubles;

@@ -92,6 +92,42 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// lane owns, for every row group rg and column block nb: row row0 + 8*rg + lane/4, columns 8*nb + 2*(lane%4) + {0,1}
+template <int T, bool FWD>
+__device__ __forceinline__ void store_outputs(const double (&acc)[4][(T + 7) / 8][2], const SweepArgs& a, int row0, int c0,
+                                              int w, int h, long long uoff, int lr, int lk) {
+  constexpr int NB = (T + 7) / 8;
+#pragma unroll
+  for (int rg = 0; rg < 4; ++rg) {
+    const int r = row0 + 8 * rg + lr;
+    double* dst = nullptr;
+    double* out = nullptr;
+    if (FWD) {
+      if (r < h) dst = (r < w) ? a.Y + (size_t)(c0 + r) * T : a.U + (size_t)(uoff + (r - w)) * T;
+    } else if (r < w) {
+      dst = a.Xp + (size_t)(c0 + r) * T;
+      out = a.Out + (size_t)a.perm[c0 + r] * a.ldo;
+    }
+    if (!dst) continue;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const int col = 8 * nb + 2 * lk;
+      if (T >= 2) {
+        if (col < T) {
+          *reinterpret_cast<double2*>(dst + col) = make_double2(acc[rg][nb][0], acc[rg][nb][1]);
+          if (out) {
+            if (col < a.t) out[col] = acc[rg][nb][0];
+            if (col + 1 < a.t) out[col + 1] = acc[rg][nb][1];
+          }
+        }
+      } else if (col == 0) {
+        dst[0] = acc[rg][nb][0];
+        if (out) out[0] = acc[rg][nb][0];
+      }
+    }
+  }
+}
+
 // One warp per short panel, or the 8 warps of a CTA on disjoint k ranges of one long panel.
 // Per warp and k-block (4 steps): 1 KB of the panel (32 B per lane, already in A-fragment order), one
 // shared-memory double per lane (B fragment of the T-wide input rows) and 4 DMMA per 8 output columns.
@@ -243,35 +279,85 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
           if (col < T) acc[rg][nb][e] = red[(8 * rg + lr) * T + col];
         }
   }
-#pragma unroll
-  for (int rg = 0; rg < 4; ++rg) {
-    const int r = row0 + 8 * rg + lr;
-    double* dst = nullptr;
-    double* out = nullptr;
-    if (FWD) {
-      if (r < h) dst = (r < w) ? a.Y + (size_t)(c0 + r) * T : a.U + (size_t)(uoff + (r - w)) * T;
-    } else if (r < w) {
-      dst = a.Xp + (size_t)(c0 + r) * T;
-      out = a.Out + (size_t)a.perm[c0 + r] * a.ldo;
-    }
-    if (!dst) continue;
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const int col = 8 * nb + 2 * lk;
-      if (T >= 2) {
-        if (col < T) {
-          *reinterpret_cast<double2*>(dst + col) = make_double2(acc[rg][nb][0], acc[rg][nb][1]);
-          if (out) {
-            if (col < a.t) out[col] = acc[rg][nb][0];
-            if (col + 1 < a.t) out[col + 1] = acc[rg][nb][1];
-          }
-        }
-      } else if (col == 0) {
-        dst[0] = acc[rg][nb][0];
-        if (out) out[0] = acc[rg][nb][0];
+  store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
+}
+
+// Tiny panels (klen <= kTinyK steps, the leaves of the elimination forest: most of the supernodes but ~10 % of
+// the data): one warp per panel, the WHOLE panel (<= 16 KB) and its input rows are copied to shared memory with
+// cp.async in one go, so 20 KB per warp are in flight and there is no per-tile latency chain; 4 warps per CTA.
+template <int T, bool FWD, int KMAX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int first, int count) {
+  constexpr int NB = (T + 7) / 8;
+  constexpr int MB = KMAX * 32;         // doubles of panel data per warp
+  constexpr int BB = KMAX * T;          // doubles of input rows per warp
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int q = blockIdx.x * WARPS + warp;
+  if (q >= count) return;
+  double* mbuf = smem + (size_t)warp * (MB + BB);
+  double* bbuf = mbuf + MB;
+  long long off;
+  int klen, c0, w, h, row0;
+  long long uoff = 0, rows_off = 0;
+  if (FWD) {
+    const FwdPanel p = reinterpret_cast<const FwdPanel*>(a.panels)[first + q];
+    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.row0; uoff = p.uoff;
+  } else {
+    const BwdPanel p = reinterpret_cast<const BwdPanel*>(a.panels)[first + q];
+    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
+  }
+  const int nkb = klen >> 2;
+  const double* base = a.data + off + lane * 4;
+  const int* rows = a.rows + rows_off;
+  for (int kb = 0; kb < nkb; ++kb) {
+    cp_async16(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128);
+    cp_async16(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2);
+  }
+  if (T >= 2) {
+    constexpr int CPR = (T >= 2) ? T / 2 : 1;
+    const int chunks = klen * CPR;
+    for (int qq = lane; qq < chunks; qq += 32) {
+      const int r = qq / CPR, part = qq % CPR;
+      const double* src;
+      if (FWD) src = a.Wk + (size_t)(c0 + r) * T;
+      else {
+        const int i = min(row0 + r, h - 1);
+        src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
       }
+      cp_async16(bbuf + (size_t)r * T + 2 * part, src + 2 * part);
+    }
+  } else {
+    for (int r = lane; r < klen; r += 32) {
+      const double* src;
+      if (FWD) src = a.Wk + (size_t)(c0 + r);
+      else { const int i = min(row0 + r, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
+      bbuf[r] = *src;
     }
   }
+  cp_async_commit();
+  double acc[4][NB][2];
+#pragma unroll
+  for (int rg = 0; rg < 4; ++rg)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
+  cp_async_wait<0>();
+  __syncwarp();
+#pragma unroll 2
+  for (int kb = 0; kb < nkb; ++kb) {
+    const double2 m0 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4);
+    const double2 m1 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4 + 2);
+    const double* brow = bbuf + (size_t)(4 * kb + lk) * T;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
+      dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
+      dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
+      dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
+      dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+    }
+  }
+  store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
 }
 
 int pick_T(int t) { return t <= 1 ? 1 : t <= 2 ? 2 : t <= 4 ? 4 : t <= 8 ? 8 : t <= 16 ? 16 : 32; }
@@ -304,6 +390,25 @@ void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
     configured = true;
   }
   sweep_kernel<T, FWD, D, NOALLOC, OCC><<<nu, kThreads, bytes, st>>>(a);
+}
+
+template <int T, bool FWD, int KMAX, int WARPS>
+void launch_tiny_one(int first, int count, cudaStream_t st, const SweepArgs& a) {
+  constexpr int bytes = WARPS * (KMAX * 32 + KMAX * T) * (int)sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(sweep_tiny_kernel<T, FWD, KMAX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    configured = true;
+  }
+  sweep_tiny_kernel<T, FWD, KMAX, WARPS><<<(count + WARPS - 1) / WARPS, WARPS * 32, bytes, st>>>(a, first, count);
+}
+
+// panels [first, first + count) are sorted by length, the last `nshort` ones have klen <= kTinyS
+template <int T, bool FWD>
+void launch_tiny(int first, int count, int nshort, cudaStream_t st, const SweepArgs& a) {
+  const int nlong = count - nshort;
+  if (nlong > 0) launch_tiny_one<T, FWD, kTinyK, 4>(first, nlong, st, a);
+  if (nshort > 0) launch_tiny_one<T, FWD, kTinyS, 8>(first + nlong, nshort, st, a);
 }
 
 template <int T, bool FWD>
@@ -374,6 +479,14 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       launch_sweep<T, true>(nu, st, a);
       PCU_LAUNCH_CHECK(c);
     }
+    if (bj->fwd_tinyn[l] > 0) {
+      prof.mark("fwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->fwd_tinyn[l]), 0.0);
+      a.panels = bj->fwd_panels;
+      a.data = bj->fwd_data;
+      launch_tiny<T, true>(bj->fwd_tiny0[l], bj->fwd_tinyn[l], bj->fwd_tinys[l], st, a);
+      c->launches++;
+      PCU_LAUNCH_CHECK(c);
+    }
   }
   for (int l = bj->nlevels - 1; l >= 0; --l) {
     const int nu = bj->bwd_unit_ptr[l + 1] - bj->bwd_unit_ptr[l];
@@ -383,6 +496,14 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       a.panels = bj->bwd_panels;
       a.data = bj->bwd_data;
       launch_sweep<T, false>(nu, st, a);
+      PCU_LAUNCH_CHECK(c);
+    }
+    if (bj->bwd_tinyn[l] > 0) {
+      prof.mark("bwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->bwd_tinyn[l]), 0.0);
+      a.panels = bj->bwd_panels;
+      a.data = bj->bwd_data;
+      launch_tiny<T, false>(bj->bwd_tiny0[l], bj->bwd_tinyn[l], bj->bwd_tinys[l], st, a);
+      c->launches++;
       PCU_LAUNCH_CHECK(c);
     }
   }
