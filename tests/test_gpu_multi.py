@@ -39,7 +39,9 @@ rhs = capi.driver_rhs(arr["m"])
 ref_rhs = np.concatenate([g["r%%d_rhs" %% r] for r in range(rank * per, (rank + 1) * per)])
 sol, hist, info = capi.solve(rhs, t, tol, ortho=int(g["ortho"]))
 ref_sol = np.concatenate([g["r%%d_sol" %% r] for r in range(rank * per, (rank + 1) * per)])
-out = {"rank": rank, "rhs_equal": bool(np.array_equal(rhs, ref_rhs)), "iter": info.iter, "ref_iter": int(g["iter"]),
+# the global norm of the rhs goes through an NCCL all-reduce whose summation order is not the rank order of
+# the golden run: the last bit of the scaled entries may differ
+out = {"rank": rank, "rhs_equal": bool(np.allclose(rhs, ref_rhs, rtol=4e-16, atol=0)), "iter": info.iter, "ref_iter": int(g["iter"]),
        "hist_dev": float(np.max(np.abs(hist[:len(g["res_hist"])] - g["res_hist"][:len(hist)]) / g["res_hist"][:len(hist)])),
        "sol_dev": float(np.linalg.norm(sol - ref_sol) / np.linalg.norm(ref_sol)), "true": info.true_relres,
        "nhalo": len(arr["halo"]), "dep": arr["dep"].tolist()}
