@@ -21,7 +21,7 @@ H_OBJS   := $(patsubst %.c,$(OBJ)/%.o,$(H_SRCS))
 
 TARGETS := $(LIB)/libmpishim.so $(LIB)/libprealps_cuda.so $(LIB)/libprealps_b200.so
 ifneq ($(wildcard $(REF)/examples/test_ecg_prealps_op.c),)
-TARGETS += $(BIN)/test_ecg_prealps_op
+TARGETS += $(BIN)/test_ecg_prealps_op $(BIN)/test_ecg_bench_fused
 endif
 
 all: $(TARGETS)
@@ -50,6 +50,10 @@ $(LIB)/libprealps_b200.so: $(H_OBJS) $(LIB)/libprealps_cuda.so $(LIB)/libmpishim
 
 # the reference driver, compiled UNCHANGED straight from the reference tree
 $(BIN)/test_ecg_prealps_op: $(REF)/examples/test_ecg_prealps_op.c $(LIB)/libprealps_b200.so | $(BIN)
+	$(CC) -O2 -std=gnu99 -w -Iinclude/compat -Iinclude -Impishim $< -o $@ -L$(LIB) -lprealps_b200 -lprealps_cuda \
+	    -lmpishim -Wl,-rpath,'$$ORIGIN/../lib' -lm
+
+$(BIN)/test_ecg_bench_fused: $(REF)/examples/test_ecg_bench_fused.c $(LIB)/libprealps_b200.so | $(BIN)
 	$(CC) -O2 -std=gnu99 -w -Iinclude/compat -Iinclude -Impishim $< -o $@ -L$(LIB) -lprealps_b200 -lprealps_cuda \
 	    -lmpishim -Wl,-rpath,'$$ORIGIN/../lib' -lm
 

@@ -162,6 +162,10 @@ int pcu_update_xr(pcu_ctx* ctx, int m, int t, const double* P, int ldp, const do
  *   Replaces dgemm at ref: ecg.c:517 (V = [P, P_prev], beta = [beta1; beta2]) and ecg.c:354. */
 int pcu_update_z(pcu_ctx* ctx, int m, int tz, double* Z, int ldz, const double* P, int ldp, int t1,
                  const double* beta1, const double* Pprev, int ldpp, int t2, const double* beta2);
+/* ORTHODIR_FUSED (ref: ecg.c:532-658): the small-matrix step U = chol_upper(mu), beta1 <- U^-T beta1 U^-1,
+ * beta2 <- beta2 U^-1 (ref: ecg.c:577-587), and Z <- Z U^-1 with U = chol_upper(G) (ref: ecg.c:583) */
+int pcu_fused_small(pcu_ctx* ctx, int t, const double* mu, double* beta1, double* beta2, double* U_out, int* status_dev);
+int pcu_right_solve(pcu_ctx* ctx, int m, int t, const double* G, double* Z, int ldz);
 /* sol[i] = sum_c X[i,c]; replaces dgemv at ref: ecg.c:674 (cplm_kernels.c:454-472) */
 int pcu_sum_columns(pcu_ctx* ctx, int m, int t, const double* X, int ldx, double* sol_dev);
 /* R[i, col_of_row[i]] = rhs[i], all else 0 (R0 = T(b), ref: ecg.c:201-221); col_of_row on device */

@@ -220,6 +220,36 @@ def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None):
     Pp, APp = np.zeros((M, t)), np.zeros((M, t))
     hist, it = [], 0
     import scipy.linalg as sla
+    if ortho == 2:
+        # _preAlps_ECGIterateOdirFused (ecg.c:532-658) inside the loop of test_ecg_bench_fused.c:245-259
+        rsolve = lambda U, B: sla.solve_triangular(U, B.T, trans="T", lower=False).T   # B U^-1
+        while True:
+            Z = prec(AP)
+            alpha = gsum(lambda r: Pk[sl[r]].T @ R[sl[r]])                          # ecg.c:557
+            b1 = gsum(lambda r: AP[sl[r]].T @ Z[sl[r]])                             # ecg.c:558 (beta = AV^T Z)
+            b2 = gsum(lambda r: APp[sl[r]].T @ Z[sl[r]])
+            mu = gsum(lambda r: AP[sl[r]].T @ Pk[sl[r]])                            # ecg.c:559
+            rtr = gsum(lambda r: R[sl[r]].T @ R[sl[r]])                             # ecg.c:560
+            res = np.sqrt(np.trace(rtr))                                            # ecg.c:566-569 (lags one iteration)
+            hist.append(res)
+            conv = res < tol * normb or it > max_iter                               # ecg.c:571
+            U = sla.cholesky(np.triu(mu) + np.triu(mu, 1).T, lower=False)           # ecg.c:577
+            Pk, AP, Z = rsolve(U, Pk), rsolve(U, AP), rsolve(U, Z)                  # ecg.c:580-583
+            b1, b2 = rsolve(U, b1), rsolve(U, b2)                                   # ecg.c:582 (whole 2t x t beta)
+            alpha = sla.solve_triangular(U, alpha, trans="T", lower=False)          # ecg.c:584
+            b1 = sla.solve_triangular(U, b1, trans="T", lower=False)                # ecg.c:586
+            Z = Z - Pk @ b1 - Pp @ b2                                               # ecg.c:590
+            X = X + Pk @ alpha                                                      # ecg.c:644-645
+            R = R - AP @ alpha
+            it += 1
+            Pp, APp, Pk = Pk, AP, Z                                                 # ecg.c:651-653
+            if conv:
+                break
+            AP = A @ Pk
+        sol = X.sum(axis=1)
+        b = np.concatenate(rhs)
+        return {"iter": it, "res_hist": np.array(hist), "sol": sol, "normb": normb,
+                "true_relres": np.linalg.norm(b - A @ sol) / np.linalg.norm(b), "rhs": rhs}
     while True:
         G = gsum(lambda r: AP[sl[r]].T @ Pk[sl[r]])                     # ecg.c:425-428
         U = sla.cholesky(np.triu(G) + np.triu(G, 1).T, lower=False)      # ecg.c:431 ('U' triangle)

@@ -797,6 +797,66 @@ __global__ void __launch_bounds__(kThreads) fro2_kernel(int m, int t, const doub
   }
 }
 
+// ORTHODIR_FUSED small-matrix step (ref: ecg.c:577-587): U = chol(mu); beta1 <- U^-T beta1 U^-1; beta2 <- beta2 U^-1
+__global__ void __launch_bounds__(kThreads) fused_small_kernel(int t, const double* __restrict__ mu, double* beta1,
+                                                               double* beta2, double* U_out, int* status) {
+  __shared__ double sU[kMaxT * kMaxT], sUi[kMaxT * kMaxT], sT[kMaxT * kMaxT], sT2[kMaxT * kMaxT];
+  __shared__ int sfail;
+  const int tid = threadIdx.x;
+  if (tid == 0) sfail = 0;
+  for (int e = tid; e < t * t; e += kThreads) sU[e] = ((e % t) <= (e / t)) ? mu[e] : 0.0;
+  __syncthreads();
+  smem_chol_upper(sU, t, &sfail);
+  smem_triu_inverse(sU, sUi, t);
+  // sT = beta1 Ui ; beta1' = Ui^T sT
+  for (int e = tid; e < t * t; e += kThreads) {
+    const int a = e % t, c = e / t;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k <= c; ++k) { s1 += beta1[a + k * t] * sUi[k + c * t]; s2 += beta2[a + k * t] * sUi[k + c * t]; }
+    sT[e] = s1;
+    sT2[e] = s2;
+  }
+  __syncthreads();
+  for (int e = tid; e < t * t; e += kThreads) {
+    const int a = e % t, c = e / t;
+    double s1 = 0.0;
+    for (int k = 0; k <= a; ++k) s1 += sUi[k + a * t] * sT[k + c * t];
+    beta1[e] = s1;
+    beta2[e] = sT2[e];
+    if (U_out) U_out[e] = ((e % t) <= (e / t)) ? sU[e] : 0.0;
+  }
+  if (tid == 0 && status) status[0] = sfail;
+}
+
+// Z <- Z U^-1 with U = chol_upper(G): row-per-thread, the t x t factor recomputed per CTA in shared memory
+template <int T>
+__global__ void __launch_bounds__(kThreads) right_solve_kernel(int m, int t, const double* __restrict__ G, double* Z, int ldz) {
+  __shared__ double sU[T * T], sUi[T * T];
+  __shared__ int sfail;
+  const int tid = threadIdx.x;
+  if (tid == 0) sfail = 0;
+  for (int e = tid; e < t * t; e += kThreads) sU[e] = ((e % t) <= (e / t)) ? G[e] : 0.0;
+  __syncthreads();
+  smem_chol_upper(sU, t, &sfail);
+  smem_triu_inverse(sU, sUi, t);
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + tid; r < m; r += (int64_t)gridDim.x * kThreads) {
+    double z[T], q[T];
+#pragma unroll
+    for (int a = 0; a < T; ++a) z[a] = (a < t) ? Z[r * ldz + a] : 0.0;
+#pragma unroll
+    for (int b = 0; b < T; ++b) {
+      double sacc = 0.0;
+      if (b < t) {
+#pragma unroll
+        for (int a = 0; a < T; ++a) if (a <= b) sacc = fma(z[a], sUi[a + b * t], sacc);
+      }
+      q[b] = sacc;
+    }
+#pragma unroll
+    for (int b = 0; b < T; ++b) if (b < t) Z[r * ldz + b] = q[b];
+  }
+}
+
 int pick_T(int t) { return t <= 1 ? 1 : t <= 2 ? 2 : t <= 4 ? 4 : t <= 8 ? 8 : t <= 16 ? 16 : 32; }
 
 }  // namespace
@@ -941,6 +1001,21 @@ int pcu_update_z(pcu_ctx* c, int m, int tz, double* Z, int ldz, const double* P,
     }
   } else
   DISPATCH_T(T, update_z_kernel<TT><<<grid, kThreads, 0, c->stream>>>(m, tz, Z, ldz, P, ldp, t1, beta1, Pp, ldpp, t2, beta2));
+  PCU_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int pcu_fused_small(pcu_ctx* c, int t, const double* mu, double* beta1, double* beta2, double* U_out, int* status_dev) {
+  PCU_CHECK(c && mu && beta1 && beta2 && t >= 1 && t <= kMaxT, "pcu_fused_small: bad arguments");
+  fused_small_kernel<<<1, kThreads, 0, c->stream>>>(t, mu, beta1, beta2, U_out, status_dev);
+  PCU_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int pcu_right_solve(pcu_ctx* c, int m, int t, const double* G, double* Z, int ldz) {
+  PCU_CHECK(c && G && Z && t >= 1 && t <= kMaxT, "pcu_right_solve: bad arguments");
+  const int grid = stream_grid(c, m, kThreads, kWaves);
+  DISPATCH_T(pick_T(t), right_solve_kernel<TT><<<grid, kThreads, 0, c->stream>>>(m, t, G, Z, ldz));
   PCU_LAUNCH_CHECK(c);
   return 0;
 }

@@ -72,6 +72,17 @@ int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int b
   preAlps_ECGInitialize(&ecg, rhs, &rci);
   const double t_init = pa_wtime();
   preAlps_BlockJacobiApply(ecg.R, ecg.P);
+  if (ecg.ortho_alg == ORTHODIR_FUSED) {
+    /* loop of the reference's examples/test_ecg_bench_fused.c:245-259 */
+    while (rci != 1) {
+      preAlps_BlockOperator(ecg.P, ecg.AP);
+      preAlps_BlockJacobiApply(ecg.AP, ecg.Z);
+      preAlps_ECGIterate(&ecg, &rci);
+      if (res_hist && nh < max_hist) res_hist[nh] = ecg.res;
+      ++nh;
+    }
+    stop = 1;
+  } else
   preAlps_BlockOperator(ecg.P, ecg.AP);
   while (stop != 1) {
     preAlps_ECGIterate(&ecg, &rci);

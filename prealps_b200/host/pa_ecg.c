@@ -53,6 +53,14 @@ static double* sm_alpha(ecg_priv_t* p) { return p->small + 3 * (size_t)p->t * p-
 static double* sm_beta1(ecg_priv_t* p) { return p->small + 4 * (size_t)p->t * p->t; }
 static double* sm_beta2(ecg_priv_t* p) { return p->small + 5 * (size_t)p->t * p->t; }
 static double* sm_rr(ecg_priv_t* p) { return p->small + 6 * (size_t)p->t * p->t; }
+/* ORTHODIR_FUSED keeps its five reduced products adjacent: alpha | beta1 | beta2 | mu | rr (one all-reduce, ref: ecg.c:563) */
+static double* fu_alpha(ecg_priv_t* p) { return p->small; }
+static double* fu_beta1(ecg_priv_t* p) { return p->small + (size_t)p->t * p->t; }
+static double* fu_beta2(ecg_priv_t* p) { return p->small + 2 * (size_t)p->t * p->t; }
+static double* fu_mu(ecg_priv_t* p) { return p->small + 3 * (size_t)p->t * p->t; }
+static double* fu_rr(ecg_priv_t* p) { return p->small + 4 * (size_t)p->t * p->t; }
+static double* fu_U(ecg_priv_t* p) { return p->small + 5 * (size_t)p->t * p->t + 8; }
+static double* fu_aout(ecg_priv_t* p) { return p->small + 6 * (size_t)p->t * p->t + 8; }
 
 static void set_shell(CPLM_Mat_Dense_t* s, double* val, int M, int m, int n, int ld) {
   CPLM_MatDenseSetInfo(s, M, n, m, n, ROW_MAJOR);
@@ -84,7 +92,7 @@ int _preAlps_ECGMalloc(preAlps_ECG_t* ecg) {
   p->owner = ecg; p->m = m; p->t = t;
   p->ld = (t % 2 == 0 || t == 1) ? t : t + 1;  /* even row stride keeps 16-byte vector access legal */
   const size_t blk = (size_t)m * p->ld;
-  const size_t smalls = 6 * (size_t)t * t + 16;
+  const size_t smalls = 8 * (size_t)t * t + 16;
   /* one pool, like the reference's mkl_calloc(7mt + 3t^2) (ref: ecg.c:58-62), but in HBM */
   ecg->work = (double*)pcu_malloc(c, sizeof(double) * (7 * blk + smalls + 8));
   if (!ecg->work) CPLM_Abort("device allocation of the ECG pool failed: %s", pcu_last_error());
@@ -173,8 +181,6 @@ int preAlps_ECGInitialize(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
                size, ecg->enlFac);
   if (ecg->bs_red == ADAPT_BS)
     CPLM_Abort("adaptive reduction of the search directions (-r 1) is not implemented in this build yet");
-  if (ecg->ortho_alg == ORTHODIR_FUSED)
-    CPLM_Abort("ORTHODIR_FUSED is not implemented in this build yet (ORTHODIR already needs one all-reduce per half step)");
   _preAlps_ECGMalloc(ecg);
   return _preAlps_ECGReset(ecg, rhs, rci_request);
 }
@@ -256,10 +262,42 @@ int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
   return 0;
 }
 
+/* ref: ecg.c:532-658.  One all-reduce per iteration: alpha = P^T R, beta = [AP^T Z; APprev^T Z], mu = AP^T P and
+ * R^T R are formed from the un-normalised blocks, reduced together, and the normalisation by U = chol(mu) is
+ * applied afterwards (P, AP, Z <- . U^-1; alpha <- U^-T alpha; beta1 <- U^-T beta1 U^-1; beta2 <- beta2 U^-1).
+ * The residual test therefore lags one iteration (ecg.c:566-574); rci_request = 1 means converged. */
 int _preAlps_ECGIterateOdirFused(preAlps_ECG_t* ecg, int* rci_request) {
-  (void)ecg; (void)rci_request;
-  CPLM_Abort("ORTHODIR_FUSED is not implemented in this build yet");
-  return 1;
+  ecg_priv_t* p = priv_of(ecg);
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, t = ecg->bs, ld = p->ld;
+  double t0 = pa_wtime();
+  pa_cuda_check(pcu_gram2(c, m, t, p->P, ld, p->R, ld, fu_alpha(p), p->AP, ld, p->P, ld, fu_mu(p)), "pcu_gram2");
+  pa_cuda_check(pcu_gram2(c, m, t, p->AP, ld, p->Z, ld, fu_beta1(p), p->APp, ld, p->Z, ld, fu_beta2(p)), "pcu_gram2");
+  pa_cuda_check(pcu_fro2(c, m, t, p->R, ld, fu_rr(p)), "pcu_fro2");
+  ecg->gemm_t += pa_wtime() - t0;
+  pa_allreduce_dev(fu_alpha(p), 4 * p->t * p->t + 1, &ecg->comm_t);
+  double rr = 0.0;
+  pa_cuda_check(pcu_d2h(c, &rr, fu_rr(p), sizeof(double)), "pcu_d2h");
+  ecg->res = sqrt(rr);
+  if (ecg->res < ecg->tol * ecg->normb || ecg->iter > ecg->maxIter) *rci_request = 1;
+  else *rci_request = 0;
+  t0 = pa_wtime();
+  pa_cuda_check(pcu_fused_small(c, t, fu_mu(p), fu_beta1(p), fu_beta2(p), fu_U(p), p->status_dev), "pcu_fused_small");
+  pa_cuda_check(pcu_right_solve(c, m, t, fu_mu(p), p->Z, ld), "pcu_right_solve");
+  /* P,AP <- .U^-1 ; alpha = U^-T alpha ; X += P alpha ; R -= AP alpha */
+  pa_cuda_check(pcu_ortho_update(c, m, t, fu_mu(p), fu_alpha(p), p->P, ld, p->AP, ld, p->X, ld, p->R, ld, NULL, fu_aout(p),
+                                 sm_rr(p), p->status_dev), "pcu_ortho_update");
+  ecg->trsm_t += pa_wtime() - t0;
+  t0 = pa_wtime();
+  pa_cuda_check(pcu_update_z(c, m, t, p->Z, ld, p->P, ld, t, fu_beta1(p), p->Pp, ld, t, fu_beta2(p)), "pcu_update_z");
+  ecg->gemm_t += pa_wtime() - t0;
+  ecg->iter++;
+  p->have_rr = 1;
+  double* oldPp = p->Pp; double* oldAPp = p->APp;
+  p->Pp = p->P; p->P = p->Z; p->Z = oldPp;
+  p->APp = p->AP; p->AP = oldAPp;
+  refresh_shells(ecg, p);
+  return 0;
 }
 
 int preAlps_ECGIterate(preAlps_ECG_t* ecg, int* rci_request) {

@@ -29,6 +29,8 @@ CASES = [
     ("poisson7_n10_s8_t2_omin", "poisson7", 10, 8, 2, 1, 1e-6),
     ("stencil27_n8_s4_t2_odir", "stencil27", 8, 4, 2, 0, 1e-8),
     ("poisson7_n9_s6_t3_odir", "poisson7", 9, 6, 3, 0, 1e-7),
+    ("poisson7_n8_s4_t4_fused", "poisson7", 8, 4, 4, 2, 1e-8),
+    ("poisson7_n12_s8_t8_fused", "poisson7", 12, 8, 8, 2, 1e-8),
 ]
 
 

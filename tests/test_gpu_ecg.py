@@ -162,3 +162,24 @@ def test_driver_error_behaviour_matches_reference():
                              timeout=300)
     assert out.returncode != 0
     assert "Enlarging factor must be lower than the number of processors" in out.stderr
+
+
+def test_unchanged_fused_bench_driver():
+    """examples/test_ecg_bench_fused.c of the reference, compiled unchanged: runs Orthodir and ORTHODIR_FUSED back to back"""
+    exe = os.path.join(ROOT, "prealps_b200", "bin", "test_ecg_bench_fused")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built")
+    g, A = load_case("poisson7_n12_s8_t8_fused")
+    g0 = np.load(os.path.join(GOLDEN, "poisson7_n12_s8_t8_odir.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        mtx = os.path.join(d, "A.mtx")
+        gen_matrices.write_mtx(mtx, A)
+        env = dict(os.environ, MPISHIM_NP="8")
+        out = subprocess.run([exe, "-e", "8", "-m", mtx, "-r", "0", "-t", "1e-8"], env=env, capture_output=True, text=True,
+                             timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    import re
+    its = [int(x) for x in re.findall(r"^\s*iter\s*:\s*(\d+)\s*$", out.stdout, flags=re.M)]
+    assert len(its) >= 2, out.stdout
+    assert abs(its[0] - int(g0["iter"])) <= 1       # Orthodir
+    assert abs(its[1] - int(g["iter"])) <= 1        # fused: one more iteration (the residual test lags)
