@@ -178,8 +178,8 @@ def test_unchanged_fused_bench_driver():
         out = subprocess.run([exe, "-e", "8", "-m", mtx, "-r", "0", "-t", "1e-8"], env=env, capture_output=True, text=True,
                              timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    # this driver prints timings only (ref: test_ecg_bench_fused.c:300-334); both solves must have run to the end
+    assert "=== ODIR ===" in out.stdout and "=== F-ODIR ===" in out.stdout
     import re
-    its = [int(x) for x in re.findall(r"^\s*iter\s*:\s*(\d+)\s*$", out.stdout, flags=re.M)]
-    assert len(its) >= 2, out.stdout
-    assert abs(its[0] - int(g0["iter"])) <= 1       # Orthodir
-    assert abs(its[1] - int(g["iter"])) <= 1        # fused: one more iteration (the residual test lags)
+    tot = [float(x) for x in re.findall(r"^\s*total\s*:\s*([0-9.e+-]+) s\s*$", out.stdout, flags=re.M)]
+    assert len(tot) == 2 and all(0 < v < 600 for v in tot)
