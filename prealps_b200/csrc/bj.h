@@ -45,10 +45,18 @@ struct BwdPanel {      // one 32-row slice of M_s^T
 constexpr int kTinyS = 16;  // ... and the very short ones get a quarter of the buffer, 4x more warps per SM
 constexpr int kTinyK = 64;  // panels up to this many steps are staged whole into shared memory
 
+constexpr int kChunkMinKB = 128;            // shortest slice (k-blocks of 4 steps) a CTA gets when a long panel is cut across CTAs
+constexpr int kTinyFold = 512;              // fewer short panels than this at a level: no separate launch for them
+constexpr int kWarpSlots = 148 * 2 * 8;     // resident warps of the sweep kernel (2 CTAs of 8 warps per SM)
+
 struct WorkUnit {      // one CTA of the sweep kernels
   int first;           // first panel
   int count;           // 1..8 panels (one per warp), or 1 panel split over all warps when split != 0
-  int split;
+  int split;           // 0: one warp per panel; 1: the 8 warps share one panel; 2: ... and only its k-blocks [kb0, kb1)
+  int kb0, kb1;        // split == 2: this CTA's slice of the panel
+  int chunk, nchunks;  // split == 2: position of the slice; the CTA that finishes last adds the slices in order
+  int slot;            // split == 2: first scratch slot of the panel (one slot = 32 x T doubles per slice); counter index in cidx
+  int cidx;
   int pad_;
 };
 
@@ -87,4 +95,8 @@ struct pcu_bj {
   double* Y = nullptr;
   double* U = nullptr;
   double* Xp = nullptr;            // solution in forest (permuted) order, read by the descendants
+  // inter-CTA split-K: partial results of the slices of one panel and one arrival counter per panel
+  double* scratch = nullptr;
+  int* counters = nullptr;
+  int scratch_slots = 0, ncounters = 0;
 };

@@ -357,7 +357,7 @@ int pcu_bj_destroy(pcu_bj* bj) {
   cudaFree(bj->fwd_data); cudaFree(bj->bwd_data); cudaFree(bj->fwd_panels); cudaFree(bj->bwd_panels);
   cudaFree(bj->fwd_units); cudaFree(bj->bwd_units); cudaFree(bj->perm); cudaFree(bj->rows);
   cudaFree(bj->lvl_cols); cudaFree(bj->gl_ptr); cudaFree(bj->gl_idx);
-  cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp);
+  cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp); cudaFree(bj->scratch); cudaFree(bj->counters);
   delete bj;
   return 0;
 }
@@ -538,10 +538,14 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   bj->bwd_tiny0.assign(nlev, 0); bj->bwd_tinyn.assign(nlev, 0);
   bj->fwd_tinys.assign(nlev, 0); bj->bwd_tinys.assign(nlev, 0);
   const bool use_tiny = getenv("PREALPS_BJ_NOTINY") == nullptr;
+  const bool use_chunks = getenv("PREALPS_BJ_NOCHUNK") == nullptr;
   auto make_units = [&](std::vector<int>& klen_of, int first, int count_all, std::vector<WorkUnit>& units, int* tiny0,
                         int* tinyn, int* tinys) {
     int count = count_all;
     if (use_tiny) while (count > 0 && klen_of[first + count - 1] <= kTinyK) --count;
+    // a handful of short panels next to longer ones ride along in the main launch (one warp each) instead of
+    // costing the level another one or two launches
+    if (count > 0 && count_all - count < kTinyFold) count = count_all;
     *tiny0 = first + count;
     *tinyn = count_all - count;
     int cs = count_all;
@@ -549,8 +553,38 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     *tinys = count_all - cs;
     // panels [first, first+count) are already sorted by klen descending
     int i = 0;
-    while (i < count && klen_of[first + i] >= kSplitK) { units.push_back({first + i, 1, 1, 0}); ++i; }
-    while (i < count) { const int c = std::min(8, count - i); units.push_back({first + i, c, 0, 0}); i += c; }
+    int slots = 0, ctrs = 0;
+    // Work per level is spread over the 148 x 2 resident CTAs x 8 warps: q = k-blocks per warp when every warp slot
+    // is busy. A panel longer than 4q gets a whole CTA (its 8 warps on disjoint k ranges), one longer than ~12q is
+    // cut across several CTAs. With many subdomains per GPU q is large and nothing is cut; with one subdomain per
+    // GPU (strong scaling) the few long panels of a level are spread over the machine instead of being streamed
+    // by one warp or one CTA each.
+    long long level_kb = 0;
+    for (int j = 0; j < count; ++j) level_kb += klen_of[first + j] / 4;
+    int split_kb = kSplitK / 4, chunk_kb = 1 << 30;
+    if (use_chunks) {
+      const int q = (int)std::max<long long>(16, (level_kb + kWarpSlots - 1) / kWarpSlots);
+      split_kb = std::min(kSplitK / 4, std::max(32, 4 * q));
+      chunk_kb = std::max(kChunkMinKB, (8 * q + 7) & ~7);
+    }
+    int nlong = 0;
+    while (nlong < count && klen_of[first + nlong] / 4 >= split_kb) ++nlong;
+    while (i < nlong) {
+      const int nkb = klen_of[first + i] / 4;
+      const int nch = (2 * nkb >= 3 * chunk_kb) ? (nkb + chunk_kb - 1) / chunk_kb : 1;
+      if (nch <= 1) units.push_back({first + i, 1, 1, 0, nkb, 0, 1, 0, 0, 0});
+      else {
+        const int per = (((nkb + nch - 1) / nch) + 7) & ~7;  // even slices, whole 8-k-block groups (one per warp)
+        for (int ch = 0; ch < nch; ++ch)
+          units.push_back({first + i, 1, 2, std::min(nkb, ch * per), std::min(nkb, (ch + 1) * per), ch, nch, slots, ctrs, 0});
+        slots += nch;
+        ++ctrs;
+      }
+      ++i;
+    }
+    bj->scratch_slots = std::max(bj->scratch_slots, slots);
+    bj->ncounters = std::max(bj->ncounters, ctrs);
+    while (i < count) { const int c = std::min(8, count - i); units.push_back({first + i, c, 0, 0, 0, 0, 1, 0, 0, 0}); i += c; }
   };
   for (int l = 0; l < nlev; ++l) {
     // forward

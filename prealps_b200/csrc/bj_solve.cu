@@ -45,10 +45,24 @@ __global__ void __launch_bounds__(kThreads) assemble_kernel(const int* __restric
     const int c0 = CPL * lig;
     if (c0 < t) a0 = src[c0];
     if (CPL == 2 && c0 + 1 < t) a1 = src[c0 + 1];
-    for (long long g = gl_ptr[c]; g < gl_ptr[c + 1]; ++g) {
-      const double* u = U + (size_t)gl_idx[g] * T + c0;
-      if (CPL == 2) { const double2 v = *reinterpret_cast<const double2*>(u); a0 -= v.x; a1 -= v.y; }
-      else a0 -= u[0];
+    // the list is walked in order (fixed summation order); 8 slots are fetched at a time so the loads overlap
+    const long long g1 = gl_ptr[c + 1];
+    for (long long g = gl_ptr[c]; g < g1; g += 8) {
+      long long idx[8];
+      double2 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) idx[j] = (g + j < g1) ? __ldg(gl_idx + g + j) : -1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = make_double2(0.0, 0.0);
+        if (idx[j] >= 0) {
+          const double* u = U + (size_t)idx[j] * T + c0;
+          if (CPL == 2) v[j] = *reinterpret_cast<const double2*>(u);
+          else v[j].x = u[0];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a0 -= v[j].x; a1 -= v[j].y; }
     }
     double* dst = Wk + (size_t)c * T + c0;
     if (CPL == 2) *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
@@ -67,6 +81,7 @@ struct SweepArgs {
   const int* rows;      // bwd gather index
   const int* perm;      // bwd: final scatter into the caller's block
   double* Out; int ldo; int t;
+  double* scratch; int* counters;   // inter-CTA split-K
 };
 
 __device__ __forceinline__ double2 ld_stream2(const double* p) {
@@ -166,10 +181,11 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
   const int nkb = klen >> 2;
   int q0 = 0, q1 = nkb;
   if (u.split) {
-    int per = (nkb + kWarps - 1) / kWarps;
+    const int s0 = (u.split == 2) ? u.kb0 : 0, s1 = (u.split == 2) ? u.kb1 : nkb;
+    int per = (s1 - s0 + kWarps - 1) / kWarps;
     per = (per + KB - 1) / KB * KB;     // whole tiles per warp
-    q0 = min(nkb, warp * per);
-    q1 = min(nkb, q0 + per);
+    q0 = min(s1, s0 + warp * per);
+    q1 = min(s1, q0 + per);
   }
   double acc[4][NB][2];
 #pragma unroll
@@ -269,6 +285,24 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
       __syncthreads();
     }
     if (warp != 0) return;
+    if (u.split == 2) {
+      // long panel cut across CTAs: publish this slice, the CTA that arrives last adds all slices in slice order
+      double* mine = a.scratch + (size_t)(u.slot + u.chunk) * 32 * T;
+      for (int e = lane; e < 32 * T; e += 32) mine[e] = red[e];
+      __threadfence();
+      int last = 0;
+      if (lane == 0) last = (atomicAdd(a.counters + u.cidx, 1) == u.nchunks - 1);
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (!last) return;
+      __threadfence();
+      if (lane == 0) a.counters[u.cidx] = 0;  // ready for the next apply
+      for (int e = lane; e < 32 * T; e += 32) {
+        double sacc = 0.0;
+        for (int ch = 0; ch < u.nchunks; ++ch) sacc += __ldcg(a.scratch + (size_t)(u.slot + ch) * 32 * T + e);
+        red[e] = sacc;
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int rg = 0; rg < 4; ++rg)
 #pragma unroll
@@ -368,6 +402,11 @@ int ensure_work(pcu_bj* bj, int T) {
   PCU_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp);
   bj->Wk = bj->Y = bj->U = bj->Xp = nullptr;
+  cudaFree(bj->scratch); cudaFree(bj->counters);
+  bj->scratch = nullptr; bj->counters = nullptr;
+  PCU_CUDA(cudaMalloc(&bj->scratch, sizeof(double) * (size_t)(bj->scratch_slots + 1) * 32 * T));
+  PCU_CUDA(cudaMalloc(&bj->counters, sizeof(int) * (size_t)(bj->ncounters + 1)));
+  PCU_CUDA(cudaMemsetAsync(bj->counters, 0, sizeof(int) * (size_t)(bj->ncounters + 1), c->stream));
   const size_t nv = ((size_t)bj->n + 72) * T, nuv = ((size_t)bj->nu + 4) * T;
   PCU_CUDA(cudaMalloc(&bj->Wk, nv * sizeof(double)));
   PCU_CUDA(cudaMalloc(&bj->Y, nv * sizeof(double)));
@@ -461,6 +500,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   SweepArgs a{};
   a.Wk = bj->Wk; a.Y = bj->Y; a.U = bj->U; a.Xp = bj->Xp; a.rows = bj->rows; a.perm = bj->perm;
   a.Out = X; a.ldo = ldx; a.t = t;
+  a.scratch = bj->scratch; a.counters = bj->counters;
   for (int l = 0; l < bj->nlevels; ++l) {
     const int ncols = bj->lvl_col_ptr[l + 1] - bj->lvl_col_ptr[l];
     if (ncols > 0) {

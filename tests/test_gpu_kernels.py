@@ -197,6 +197,31 @@ def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t):
     cu.pcu_bj_destroy(bj)
 
 
+def test_block_jacobi_long_panels_cut_across_ctas(dev):
+    """a block large enough for separators beyond 1024 columns: exercises the inter-CTA split of long panels"""
+    import scipy.sparse.linalg as spla
+    A = gen_matrices.poisson7(36).tocsr()
+    n = A.shape[0]
+    U = sp.triu(A, format="csr"); U.sort_indices()
+    k = (U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data.copy())
+    rp = (C.POINTER(C.c_int) * 1)(capi.ip(k[0])); ci = (C.POINTER(C.c_int) * 1)(capi.ip(k[1]))
+    vv = (C.POINTER(C.c_double) * 1)(capi.dp(k[2]))
+    bj = C.c_void_p()
+    assert cu.pcu_bj_create(dev.ctx, 1, capi.ip(np.array([0, n], np.int32)), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
+    rng = np.random.default_rng(3)
+    lu = spla.splu(A.tocsc())
+    for t in (8, 4, 16):
+        B = rng.standard_normal((n, t))
+        dB, dX = dev.up(B), dev.zeros(n * t)
+        for rep in range(2):  # the second apply re-uses the arrival counters
+            assert cu.pcu_bj_apply(bj, dB, t, dX, t, t) == 0, cu.pcu_last_error()
+            X = dev.down(dX, (n, t))
+            ref = lu.solve(B)
+            assert np.linalg.norm(X - ref) / np.linalg.norm(ref) < 1e-11
+        dev.free(dB, dX)
+    cu.pcu_bj_destroy(bj)
+
+
 def test_block_jacobi_rejects_indefinite_block(dev):
     A = (gen_matrices.poisson7(5) - 7.0 * sp.eye(125)).tocsr()
     U = sp.triu(A, format="csr"); U.sort_indices()

@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from prealps_b200 import capi  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3, 4]
-assert capi.lib.preAlps_b200_OperatorBuildStencil(0, n, 8, 0, 8) == 0
+nsub = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+assert capi.lib.preAlps_b200_OperatorBuildStencil(0, n, nsub, 0, nsub) == 0
 assert capi.lib.preAlps_b200_BlockJacobiCreate() == 0
 for t in (8,):
     for v in variants:
