@@ -65,6 +65,9 @@ typedef struct {
 } preAlps_b200_SolveInfo;
 int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int bs_red, double* rhs,
                        double* sol, double* res_hist, int max_hist, preAlps_b200_SolveInfo* info);
+/* block size (ecg.bs) after every iteration of the last preAlps_b200_Solve: shrinks with bs_red = 1 (ADAPT_BS);
+ * copies at most `max` entries, returns the number recorded */
+int preAlps_b200_LastBlockSizes(int* out, int max);
 /* benchmark region: `warmup` then `steps` ECG iterations (restarting converged solves), device
  * resident, timed with CUDA events on the library stream.  ms_out = time of the `steps` iterations. */
 int preAlps_b200_BenchIterations(int enlFac, double tol, int ortho_alg, double* rhs, int warmup, int steps,

@@ -45,6 +45,10 @@ int pcu_memset(pcu_ctx* ctx, void* dptr, int byte, size_t bytes);
 int pcu_h2d(pcu_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);  /* synchronous */
 int pcu_d2h(pcu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* synchronous */
 int pcu_d2d(pcu_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+/* the first ncols columns of a row-major m x * device block: dst <- src (replaces the column-range
+ * mkl_domatcopy of ref: ecg.c:521-523 once the block size has been reduced) / dst <- 0 */
+int pcu_copy_cols(pcu_ctx* ctx, int m, int ncols, double* dst, int ldd, const double* src, int lds);
+int pcu_zero_cols(pcu_ctx* ctx, int m, int ncols, double* dst, int ldd);
 void* pcu_host_alloc(size_t bytes);              /* pinned host memory */
 int pcu_host_free(void* p);
 

@@ -184,6 +184,90 @@ class Partitioned:
         return sol
 
 
+def ecg_solve_adapt(P, t, tol, max_iter=1000, rhs=None):
+    """_preAlps_ECGIterateOdir with bs_red = ADAPT_BS (ecg.c:402-530, reduction at :445-497) inside the driver
+    loop of test_ecg_prealps_op.c:203-223.  The reference keeps V = [slot0 | slot1] and AV as two slots of nrhs
+    columns each (ecg.c:126-136); the live search directions are the first bs columns of slot0, the columns
+    [bs, nrhs) of slot0 hold every direction discarded so far (they stay in the A-orthogonalisation), slot1 holds
+    the previous directions.  beta = AV[:, :kbs]^T Z and Z -= V[:, :kbs] beta use kbs = nrhs + (block size before
+    the last reduction) columns (ecg.c:491-496); the end-of-iteration copies move bs columns (ecg.c:521-523).
+    Returns the block-size history as well."""
+    import scipy.linalg as sla
+    S, rowPos, M = P.S, P.rowPos, P.Ap.shape[0]
+    sizes = [rowPos[r + 1] - rowPos[r] for r in range(S)]
+    if rhs is None:
+        rhs = driver_rhs(sizes)
+    if S < t:
+        raise ValueError("Enlarging factor must be lower than the number of processors")
+    sl = [slice(rowPos[r], rowPos[r + 1]) for r in range(S)]
+    lus = P.block_solvers()
+    A = P.Ap
+    nrhs = t
+
+    def gsum(f):
+        acc = f(0)
+        for r in range(1, S):
+            acc = acc + f(r)
+        return acc
+
+    def prec(B):
+        Z = np.empty_like(B)
+        for r in range(S):
+            Z[sl[r]] = lus[r].solve(B[sl[r]])
+        return Z
+
+    normb = np.sqrt(gsum(lambda r: float(np.sum(rhs[r] ** 2))))
+    R = np.zeros((M, nrhs))
+    for r in range(S):
+        R[sl[r], r % nrhs] = rhs[r]
+    X = np.zeros((M, nrhs))
+    V = np.zeros((M, 2 * nrhs)); AV = np.zeros((M, 2 * nrhs))
+    V[:, :nrhs] = prec(R)
+    AV[:, :nrhs] = A @ V[:, :nrhs]
+    bs, kbs = nrhs, 2 * nrhs
+    cut = tol * normb / np.sqrt(nrhs)                                    # ecg.c:420
+    hist, bs_hist, it = [], [], 0
+    while True:
+        tt = bs                                                          # t = P->info.n
+        Pk, AP = V[:, :tt], AV[:, :tt]                                   # views: updates are in place
+        G = gsum(lambda r: AP[sl[r]].T @ Pk[sl[r]])
+        U = sla.cholesky(np.triu(G) + np.triu(G, 1).T, lower=False)
+        Pk[:] = sla.solve_triangular(U, Pk.T, trans="T", lower=False).T
+        AP[:] = sla.solve_triangular(U, AP.T, trans="T", lower=False).T
+        alpha = gsum(lambda r: Pk[sl[r]].T @ R[sl[r]])                   # tt x nrhs
+        Us, sv, _ = np.linalg.svd(alpha, full_matrices=True)             # ecg.c:455 (dgesvd 'O': U overwrites)
+        t1 = 0
+        for sgm in sv[:tt]:
+            if sgm > cut:
+                t1 += 1
+            else:
+                break                                                    # ecg.c:460-464
+        if 0 < t1 < nrhs and t1 < tt:                                    # ecg.c:467
+            Q = Us                                                       # geqrf of an orthogonal matrix: Q = U diag(+-1)
+            alpha = (Q.T @ alpha)[:t1]                                   # ecg.c:474,483
+            Pk[:] = Pk @ Q                                               # ecg.c:476-479 (all tt columns rotated,
+            AP[:] = AP @ Q                                               #  the last tt - t1 stay in the slot)
+            bs, kbs = t1, tt + nrhs                                      # ecg.c:491-492
+        X = X + V[:, :bs] @ alpha                                        # ecg.c:500-501
+        R = R - AV[:, :bs] @ alpha
+        it += 1
+        res = np.sqrt(np.trace(gsum(lambda r: R[sl[r]].T @ R[sl[r]])))
+        hist.append(res); bs_hist.append(bs)
+        if not (res > normb * tol and it < max_iter and bs > 0):         # ecg.c:264
+            break
+        Z = prec(AV[:, :bs])                                             # test_ecg_prealps_op.c:219
+        beta = gsum(lambda r: AV[sl[r], :kbs].T @ Z[sl[r]])              # ecg.c:510-514
+        Z = Z - V[:, :kbs] @ beta                                        # ecg.c:517
+        V[:, nrhs:nrhs + bs] = V[:, :bs]                                 # ecg.c:521-523
+        AV[:, nrhs:nrhs + bs] = AV[:, :bs]
+        V[:, :bs] = Z
+        AV[:, :bs] = A @ V[:, :bs]                                       # test_ecg_prealps_op.c:212
+    sol = X.sum(axis=1)
+    b = np.concatenate(rhs)
+    return {"iter": it, "res_hist": np.array(hist), "bs_hist": np.array(bs_hist), "sol": sol, "normb": normb,
+            "true_relres": np.linalg.norm(b - A @ sol) / np.linalg.norm(b), "rhs": rhs}
+
+
 def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None):
     """_preAlps_ECGIterateOdir / Omin with the driver loop (ecg.c:98-171,223-271,289-530;
     test_ecg_prealps_op.c:203-223), NO_BS_RED.  Global arrays; reductions summed over ranks in rank order

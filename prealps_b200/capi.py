@@ -144,6 +144,13 @@ def solve(rhs, t, tol, max_iter=1000, ortho=0, bs_red=0, max_hist=2000):
     return sol, hist[:min(info.nhist, max_hist)].copy(), info
 
 
+def last_block_sizes():
+    """ecg.bs after every iteration of the last solve()"""
+    buf = np.zeros(4096, dtype=np.int32)
+    n = lib.preAlps_b200_LastBlockSizes(ip(buf), C.c_int(buf.size))
+    return buf[:min(n, buf.size)].copy()
+
+
 def block_operator_host(X):
     """AX = A X for a host (m x t) array through preAlps_BlockOperator (staged through HBM)."""
     X = np.ascontiguousarray(X, dtype=np.float64)

@@ -176,6 +176,19 @@ int pcu_d2d(pcu_ctx* c, void* dst, const void* src, size_t bytes) {
   PCU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
   return 0;
 }
+int pcu_copy_cols(pcu_ctx* c, int m, int ncols, double* dst, int ldd, const double* src, int lds) {
+  PCU_CHECK(c && dst && src && m >= 0 && ncols >= 0 && ldd >= ncols && lds >= ncols, "pcu_copy_cols: bad arguments");
+  if (m == 0 || ncols == 0) return 0;
+  PCU_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)ldd, src, sizeof(double) * (size_t)lds,
+                             sizeof(double) * (size_t)ncols, (size_t)m, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+int pcu_zero_cols(pcu_ctx* c, int m, int ncols, double* dst, int ldd) {
+  PCU_CHECK(c && dst && m >= 0 && ncols >= 0 && ldd >= ncols, "pcu_zero_cols: bad arguments");
+  if (m == 0 || ncols == 0) return 0;
+  PCU_CUDA(cudaMemset2DAsync(dst, sizeof(double) * (size_t)ldd, 0, sizeof(double) * (size_t)ncols, (size_t)m, c->stream));
+  return 0;
+}
 void* pcu_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -58,6 +58,15 @@ static void fill_ecg(preAlps_ECG_t* ecg, int enlFac, double tol, int maxIter, in
   ecg->bs_red = (bs_red == 0 ? NO_BS_RED : ADAPT_BS);
 }
 
+static int g_bs_hist[4096];
+static int g_bs_nhist = 0;
+
+int preAlps_b200_LastBlockSizes(int* out, int max) {
+  const int n = g_bs_nhist < max ? g_bs_nhist : max;
+  for (int i = 0; i < n; ++i) out[i] = g_bs_hist[i];
+  return g_bs_nhist;
+}
+
 int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int bs_red, double* rhs, double* sol,
                        double* res_hist, int max_hist, preAlps_b200_SolveInfo* info) {
   pa_state_t* g = &pa_g;
@@ -66,6 +75,7 @@ int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int b
   preAlps_ECG_t ecg;
   fill_ecg(&ecg, enlFac, tol, maxIter, ortho_alg, bs_red);
   int rci = 0, stop = 0, nh = 0;
+  g_bs_nhist = 0;
   pa_cuda_check(pcu_sync(c), "pcu_sync");
   const double t0 = pa_wtime();
   pcu_timer_start(c, 0);
@@ -79,6 +89,7 @@ int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int b
       preAlps_BlockJacobiApply(ecg.AP, ecg.Z);
       preAlps_ECGIterate(&ecg, &rci);
       if (res_hist && nh < max_hist) res_hist[nh] = ecg.res;
+      if (g_bs_nhist < 4096) g_bs_hist[g_bs_nhist++] = ecg.bs;
       ++nh;
     }
     stop = 1;
@@ -91,6 +102,7 @@ int preAlps_b200_Solve(int enlFac, double tol, int maxIter, int ortho_alg, int b
     } else if (rci == 1) {
       preAlps_ECGStoppingCriterion(&ecg, &stop);
       if (res_hist && nh < max_hist) res_hist[nh] = ecg.res;
+      if (g_bs_nhist < 4096) g_bs_hist[g_bs_nhist++] = ecg.bs;
       ++nh;
       if (stop == 1) break;
       if (ecg.ortho_alg == ORTHOMIN) preAlps_BlockJacobiApply(ecg.R, ecg.Z);

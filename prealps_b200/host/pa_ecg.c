@@ -17,6 +17,11 @@
  *     the three block copies of ecg.c:521-523 become a pointer rotation.
  * alpha = U^{-T}(P_old^T R) equals (P U^{-1})^T R of the reference in exact arithmetic; the
  * rounding differs at the 1e-16 level ("parity").
+ *
+ * ADAPT_BS with Orthodir (ref: ecg.c:445-497), see adapt_half_step(): until the first reduction the
+ * iteration is the one above plus a t x t SVD on the host; from the first reduction on the blocks keep
+ * the reference's slot layout (V = [slot0 | slot1], live directions first, discarded ones behind them)
+ * and the copies of ecg.c:521-523 are real column-range copies.
  */
 #include "pa_internal.h"
 
@@ -36,6 +41,9 @@ typedef struct {
   int* status_dev;
   int have_rr;
   int iter_since_reset;
+  /* ADAPT_BS: after the first reduction the buffers stop rotating (slot0 = P/AP, slot1 = Pp/APp) */
+  int adapt, fixed;
+  int tprev;            /* columns of slot1 that still take part in the A-orthogonalisation (kbs - t) */
 } ecg_priv_t;
 
 #define MAX_SOLVERS 16
@@ -167,6 +175,9 @@ int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   ecg->beta->val = sm_beta1(p);
   p->have_rr = 0;
   p->iter_since_reset = 0;
+  p->adapt = (ecg->bs_red == ADAPT_BS);
+  p->fixed = 0;
+  p->tprev = t;
   *rci_request = 0;
   return 0;
 }
@@ -179,8 +190,8 @@ int preAlps_ECGInitialize(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   if (size < ecg->enlFac)
     CPLM_Abort("Enlarging factor must be lower than the number of processors in the MPI communicator! size: %d ; enlarging factor: %d",
                size, ecg->enlFac);
-  if (ecg->bs_red == ADAPT_BS)
-    CPLM_Abort("adaptive reduction of the search directions (-r 1) is not implemented in this build yet");
+  if (ecg->bs_red == ADAPT_BS && ecg->ortho_alg != ORTHODIR)
+    CPLM_Abort("adaptive reduction of the search directions (-r 1) is implemented for ORTHODIR (-o 0) only in this build");
   _preAlps_ECGMalloc(ecg);
   return _preAlps_ECGReset(ecg, rhs, rci_request);
 }
@@ -211,13 +222,208 @@ static void descent_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   p->iter_since_reset++;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * ADAPT_BS: small dense algebra on the host (t <= 32, column-major) -- stands in for LAPACKE_dpotrf,
+ * cblas_dtrsm, LAPACKE_dgesvd('O','N'), dgeqrf and dormqr on t x t data (ref: ecg.c:431-479).
+ * ------------------------------------------------------------------------------------------------ */
+static int h_chol_upper(int n, double* A, int lda) {  /* A = U^T U, upper triangle in place */
+  for (int j = 0; j < n; ++j) {
+    double d = A[j + (size_t)lda * j];
+    for (int k = 0; k < j; ++k) d -= A[k + (size_t)lda * j] * A[k + (size_t)lda * j];
+    if (!(d > 0.0)) return j + 1;
+    d = sqrt(d);
+    A[j + (size_t)lda * j] = d;
+    for (int c = j + 1; c < n; ++c) {
+      double v = A[j + (size_t)lda * c];
+      for (int k = 0; k < j; ++k) v -= A[k + (size_t)lda * j] * A[k + (size_t)lda * c];
+      A[j + (size_t)lda * c] = v / d;
+    }
+  }
+  return 0;
+}
+
+static void h_triu_inv(int n, const double* U, int ldu, double* Ui, int ldi) {
+  for (int j = 0; j < n; ++j) {
+    for (int i = 0; i < n; ++i) Ui[i + (size_t)ldi * j] = 0.0;
+    Ui[j + (size_t)ldi * j] = 1.0 / U[j + (size_t)ldu * j];
+    for (int i = j - 1; i >= 0; --i) {
+      double v = 0.0;
+      for (int k = i + 1; k <= j; ++k) v += U[i + (size_t)ldu * k] * Ui[k + (size_t)ldi * j];
+      Ui[i + (size_t)ldi * j] = -v / U[i + (size_t)ldu * i];
+    }
+  }
+}
+
+/* Left singular vectors and singular values of the t x n matrix A (column-major, lda): one-sided Jacobi on
+ * the rows of A.  On return rows[i*n .. i*n+n) = i-th row of Q^T A (row-major), sv descending, Q t x t
+ * column-major (ldq = t). */
+static void h_left_svd(int t, int n, const double* A, int lda, double* sv, double* Q, double* rows) {
+  for (int i = 0; i < t; ++i) for (int c = 0; c < n; ++c) rows[(size_t)i * n + c] = A[i + (size_t)lda * c];
+  for (int i = 0; i < t * t; ++i) Q[i] = 0.0;
+  for (int i = 0; i < t; ++i) Q[i + (size_t)t * i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    int rotated = 0;
+    for (int i = 0; i < t - 1; ++i)
+      for (int j = i + 1; j < t; ++j) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double x = rows[(size_t)i * n + k], y = rows[(size_t)j * n + k];
+          a += x * x; b += y * y; c += x * y;
+        }
+        if (fabs(c) <= 1e-15 * sqrt(a * b) || c == 0.0) continue;
+        rotated = 1;
+        const double zeta = (b - a) / (2.0 * c);
+        const double tg = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + tg * tg), sn = cs * tg;
+        for (int k = 0; k < n; ++k) {
+          const double x = rows[(size_t)i * n + k], y = rows[(size_t)j * n + k];
+          rows[(size_t)i * n + k] = cs * x - sn * y;
+          rows[(size_t)j * n + k] = sn * x + cs * y;
+        }
+        for (int k = 0; k < t; ++k) {
+          const double x = Q[k + (size_t)t * i], y = Q[k + (size_t)t * j];
+          Q[k + (size_t)t * i] = cs * x - sn * y;
+          Q[k + (size_t)t * j] = sn * x + cs * y;
+        }
+      }
+    if (!rotated) break;
+  }
+  for (int i = 0; i < t; ++i) {
+    double a = 0.0;
+    for (int k = 0; k < n; ++k) a += rows[(size_t)i * n + k] * rows[(size_t)i * n + k];
+    sv[i] = sqrt(a);
+  }
+  for (int i = 0; i < t - 1; ++i) {  /* selection sort, descending; rows and columns of Q follow */
+    int best = i;
+    for (int j = i + 1; j < t; ++j) if (sv[j] > sv[best]) best = j;
+    if (best == i) continue;
+    double tmp = sv[i]; sv[i] = sv[best]; sv[best] = tmp;
+    for (int k = 0; k < n; ++k) { tmp = rows[(size_t)i * n + k]; rows[(size_t)i * n + k] = rows[(size_t)best * n + k]; rows[(size_t)best * n + k] = tmp; }
+    for (int k = 0; k < t; ++k) { tmp = Q[k + (size_t)t * i]; Q[k + (size_t)t * i] = Q[k + (size_t)t * best]; Q[k + (size_t)t * best] = tmp; }
+  }
+}
+
+/* The "rci_request == 0" half of an Orthodir iteration with ADAPT_BS (ref: ecg.c:421-507).
+ *
+ * Layout: slot0 = (p->P, p->AP) holds [live directions (bs) | every direction discarded so far], slot1 =
+ * (p->Pp, p->APp) the previous directions; both T = enlFac columns wide. All block kernels run at the full
+ * width T on zero/identity padded small matrices, which is exact: discarded columns are multiplied by the
+ * identity, padded rows of alpha are zero. SpMM and block-Jacobi -- where the time goes -- run on bs columns
+ * because the shells handed to the caller say n = bs.
+ *
+ *   G = AP^T P, Gpr = P^T R at width T; all-reduce; read back
+ *   host: U = chol(G[:bs,:bs]); alpha = U^-T Gpr[:bs,:]; SVD(alpha) -> t1 = #{sigma > tol*normb/sqrt(T)}
+ *   no reduction and no reduction so far: the NO_BS_RED pass (pcu_ortho_update)
+ *   otherwise: W = U^-1 Q (Q = left singular vectors; the reference applies the same Q through
+ *     dgeqrf/dormqr, ecg.c:470-479 -- equal up to the signs of the columns, which cancel in P alpha)
+ *     slot0 <- slot0 * diag(W, I);  X += slot0 * [Q^T alpha (first t1 rows); 0];  R -= A slot0 * [..]
+ *     bs = t1, kbs = T + (bs before) (ecg.c:491-492): the columns of slot1 beyond the old bs leave the
+ *     A-orthogonalisation for good and are zeroed. */
+static void adapt_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, T = p->t, ld = p->ld, bs = ecg->bs;
+  double t0 = pa_wtime();
+  pa_cuda_check(pcu_gram2(c, m, T, p->AP, ld, p->P, ld, sm_G(p), p->P, ld, p->R, ld, sm_Gpr(p)), "pcu_gram2");
+  ecg->gemm_t += pa_wtime() - t0;
+  pa_allreduce_dev(sm_G(p), 2 * T * T, &ecg->comm_t);
+  double G[2 * 32 * 32], Ui[32 * 32], alpha[32 * 32], Q[32 * 32], rows[32 * 32], sv[32];
+  pa_cuda_check(pcu_d2h(c, G, sm_G(p), sizeof(double) * 2 * (size_t)T * T), "pcu_d2h");
+  const double* Gpr = G + (size_t)T * T;
+  t0 = pa_wtime();
+  h_chol_upper(bs, G, T);  /* Orthodir ignores dpotrf's return code (ref: ecg.c:431) */
+  ecg->potrf_t += pa_wtime() - t0;
+  t0 = pa_wtime();
+  h_triu_inv(bs, G, T, Ui, bs);
+  for (int j = 0; j < T; ++j)      /* alpha = U^-T Gpr[:bs, :] (bs x T, ld bs) */
+    for (int i = 0; i < bs; ++i) {
+      double v = 0.0;
+      for (int k = 0; k <= i; ++k) v += Ui[k + (size_t)bs * i] * Gpr[k + (size_t)T * j];
+      alpha[i + (size_t)bs * j] = v;
+    }
+  ecg->trsm_t += pa_wtime() - t0;
+  t0 = pa_wtime();
+  h_left_svd(bs, T, alpha, bs, sv, Q, rows);
+  ecg->gesvd_t += pa_wtime() - t0;
+  const double cut = ecg->tol * ecg->normb / sqrt((double)T);  /* ref: ecg.c:420 */
+  int t1 = 0;
+  for (int i = 0; i < bs; ++i) { if (sv[i] > cut) t1++; else break; }  /* ref: ecg.c:460-464 */
+  const int reduce = (t1 > 0 && t1 < T && t1 < bs);                     /* ref: ecg.c:467 */
+  if (!reduce && !p->fixed) {
+    t0 = pa_wtime();
+    pa_cuda_check(pcu_ortho_update(c, m, T, sm_G(p), sm_Gpr(p), p->P, ld, p->AP, ld, p->X, ld, p->R, ld, sm_U(p),
+                                   sm_alpha(p), sm_rr(p), p->status_dev), "pcu_ortho_update");
+    ecg->trsm_t += pa_wtime() - t0;
+  } else {
+    /* Wneg = -diag(W, I) and Af = [alpha'; 0], T x T column-major */
+    double Wneg[32 * 32], Af[32 * 32];
+    for (int i = 0; i < T * T; ++i) { Wneg[i] = 0.0; Af[i] = 0.0; }
+    for (int j = 0; j < T; ++j) Wneg[j + (size_t)T * j] = -1.0;
+    const int keep = reduce ? t1 : bs;
+    for (int j = 0; j < bs; ++j)
+      for (int i = 0; i < bs; ++i) {
+        double v = 0.0;
+        if (reduce) { for (int k = i; k < bs; ++k) v += Ui[i + (size_t)bs * k] * Q[k + (size_t)bs * j]; }
+        else v = Ui[i + (size_t)bs * j];
+        Wneg[i + (size_t)T * j] = -v;
+      }
+    for (int j = 0; j < T; ++j)
+      for (int i = 0; i < keep; ++i) Af[i + (size_t)T * j] = reduce ? rows[(size_t)i * T + j] : alpha[i + (size_t)bs * j];
+    pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
+    pa_cuda_check(pcu_h2d(c, sm_alpha(p), Af, sizeof(double) * (size_t)T * T), "pcu_h2d");
+    t0 = pa_wtime();
+    const size_t blk = sizeof(double) * (size_t)m * ld;
+    /* Z is free between the end of one iteration and the next preconditioner call: scratch for slot0 * W */
+    pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");
+    pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->P, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
+    pa_cuda_check(pcu_d2d(c, p->P, p->Z, blk), "pcu_d2d");
+    pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");
+    pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->AP, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
+    pa_cuda_check(pcu_d2d(c, p->AP, p->Z, blk), "pcu_d2d");
+    pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");  /* columns >= bs of Z stay zero from here on */
+    ecg->ormqr_t += pa_wtime() - t0;
+    t0 = pa_wtime();
+    pa_cuda_check(pcu_update_xr(c, m, T, p->P, ld, p->AP, ld, sm_alpha(p), p->X, ld, p->R, ld, sm_rr(p)), "pcu_update_xr");
+    ecg->gemm_t += pa_wtime() - t0;
+    if (reduce) {
+      ecg->bs = t1;
+      ecg->kbs = bs + T;
+      p->tprev = bs;
+      p->fixed = 1;
+      pa_cuda_check(pcu_zero_cols(c, m, T - bs, p->Pp + bs, ld), "pcu_zero_cols");
+      pa_cuda_check(pcu_zero_cols(c, m, T - bs, p->APp + bs, ld), "pcu_zero_cols");
+      refresh_shells(ecg, p);
+    }
+  }
+  p->have_rr = 1;
+  ecg->iter++;
+  p->iter_since_reset++;
+}
+
 int _preAlps_ECGIterateOdir(preAlps_ECG_t* ecg, int* rci_request) {
   ecg_priv_t* p = priv_of(ecg);
   pcu_ctx* c = pa_g.ctx;
   const int m = p->m, t = ecg->bs, ld = p->ld;
   if (*rci_request == 0) {
-    descent_half_step(ecg, p);
+    if (p->adapt) adapt_half_step(ecg, p);
+    else descent_half_step(ecg, p);
     *rci_request = 1;
+  } else if (*rci_request == 1 && p->fixed) {
+    /* after a reduction: beta = AV[:, :kbs]^T Z, Z -= V[:, :kbs] beta at the full width T -- the columns of Z
+     * beyond bs and the columns of slot1 beyond kbs - T are zero -- then the copies of ref: ecg.c:521-523 */
+    const int T = p->t, bs = ecg->bs;
+    double t0 = pa_wtime();
+    pa_cuda_check(pcu_gram2(c, m, T, p->AP, ld, p->Z, ld, sm_beta1(p), p->APp, ld, p->Z, ld, sm_beta2(p)), "pcu_gram2");
+    ecg->gemm_t += pa_wtime() - t0;
+    pa_allreduce_dev(sm_beta1(p), 2 * T * T, &ecg->comm_t);
+    t0 = pa_wtime();
+    pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->P, ld, T, sm_beta1(p), p->Pp, ld, T, sm_beta2(p)), "pcu_update_z");
+    ecg->gemm_t += pa_wtime() - t0;
+    t0 = pa_wtime();
+    pa_cuda_check(pcu_copy_cols(c, m, bs, p->Pp, ld, p->P, ld), "pcu_copy_cols");
+    pa_cuda_check(pcu_copy_cols(c, m, bs, p->APp, ld, p->AP, ld), "pcu_copy_cols");
+    pa_cuda_check(pcu_copy_cols(c, m, bs, p->P, ld, p->Z, ld), "pcu_copy_cols");
+    ecg->copy_t += pa_wtime() - t0;
+    *rci_request = 0;
   } else if (*rci_request == 1) {
     double t0 = pa_wtime();
     pa_cuda_check(pcu_gram2(c, m, t, p->AP, ld, p->Z, ld, sm_beta1(p), p->APp, ld, p->Z, ld, sm_beta2(p)), "pcu_gram2");

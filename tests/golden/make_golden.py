@@ -8,7 +8,7 @@ parity tests compare against into tests/golden/*.npz:
   iteration count, solution, true residual.
 Only this script needs /root/reference; the .npz files travel with the repo.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case names ...]
 """
 import json
 import os
@@ -31,6 +31,10 @@ CASES = [
     ("poisson7_n9_s6_t3_odir", "poisson7", 9, 6, 3, 0, 1e-7),
     ("poisson7_n8_s4_t4_fused", "poisson7", 8, 4, 4, 2, 1e-8),
     ("poisson7_n12_s8_t8_fused", "poisson7", 12, 8, 8, 2, 1e-8),
+    # ADAPT_BS (-r 1): the block size shrinks while the iteration goes on (bs_hist)
+    ("poisson7_n12_s8_t8_odir_adapt", "poisson7", 12, 8, 8, 0, 1e-8, 1),
+    ("elasticity3d_766_s8_t8_odir_adapt", "elasticity3d", (7, 6, 6), 8, 8, 0, 1e-8, 1),
+    ("elasticity3d_655_s4_t4_odir_adapt", "elasticity3d", (6, 5, 5), 4, 4, 0, 1e-8, 1),
 ]
 
 
@@ -42,19 +46,25 @@ def main():
     exe = os.path.join(ROOT, "oracle", "_ref", "ecg_dump_ref")
     if not os.path.exists(exe):
         sys.exit("build the oracle first: make -C oracle")
-    for name, gen, N, S, t, ortho, tol in CASES:
+    only = sys.argv[1:]
+    for case in CASES:
+        name, gen, N, S, t, ortho, tol = case[:7]
+        bs_red = case[7] if len(case) > 7 else 0
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as d:
             mtx = os.path.join(d, "A.mtx")
-            A = getattr(gen_matrices, gen)(N)
+            A = getattr(gen_matrices, gen)(*N) if isinstance(N, tuple) else getattr(gen_matrices, gen)(N)
             gen_matrices.write_mtx(mtx, A)
             env = dict(os.environ, MPISHIM_NP=str(S))
-            subprocess.run([exe, "-m", mtx, "-e", str(t), "-o", str(ortho), "-r", "0", "-t", repr(tol), "-d", d],
+            subprocess.run([exe, "-m", mtx, "-e", str(t), "-o", str(ortho), "-r", str(bs_red), "-t", repr(tol), "-d", d],
                            check=True, env=env, stdout=subprocess.DEVNULL)
-            out = {"gen": gen, "N": N, "S": S, "t": t, "ortho": ortho, "tol": tol}
+            out = {"gen": gen, "N": np.array(N), "S": S, "t": t, "ortho": ortho, "tol": tol, "bs_red": bs_red}
             summ = json.load(open(os.path.join(d, "summary.json")))
             for k in ("iter", "res", "normb", "true_relres", "M"):
                 out[k] = summ[k]
             out["res_hist"] = np.array(summ["res_hist"])
+            out["bs_hist"] = np.array(summ["bs_hist"], dtype=np.int32)
             out["perm"] = load(d, "perm.i32", np.int32)
             out["posB"] = load(d, "posB.i32", np.int32)
             out["S_rowPtr"] = load(d, "S_rowPtr.i32", np.int32)

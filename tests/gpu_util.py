@@ -12,7 +12,7 @@ from prealps_b200 import capi
 
 def load_case(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    A = getattr(gen_matrices, str(g["gen"]))(int(g["N"])).tocsr()
+    A = gen_matrices.build(g["gen"], g["N"]).tocsr()
     return g, A
 
 

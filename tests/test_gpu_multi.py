@@ -29,7 +29,7 @@ uid = uid.cuda(); dist.broadcast(uid, 0)
 assert capi.lib.preAlps_b200_InitNccl(world, rank, bytes(uid.cpu().tolist())) == 0
 g = np.load(os.path.join(%(root)r, "tests", "golden", %(case)r + ".npz"))
 S, t, tol = int(g["S"]), int(g["t"]), float(g["tol"])
-A = getattr(gen_matrices, str(g["gen"]))(int(g["N"])).tocsr(); A.sort_indices()
+A = gen_matrices.build(g["gen"], g["N"]).tocsr(); A.sort_indices()
 rp, ci, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
 per = S // world
 assert capi.lib.preAlps_b200_OperatorBuildCSR(A.shape[0], capi.ip(rp), capi.ip(ci), capi.dp(v), S, rank * per, (rank + 1) * per, 1, None) == 0

@@ -16,7 +16,7 @@ lib = capi.lib
 
 def _pipeline(g):
     """load -> scale -> k-way -> perm -> permute, all through the library's C functions"""
-    A = getattr(gen_matrices, str(g["gen"]))(int(g["N"]))
+    A = gen_matrices.build(g["gen"], g["N"])
     S = int(g["S"])
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "A.mtx")
@@ -102,7 +102,7 @@ def test_loader_general_and_zero_based(tmp_path):
     coo = A.tocoo()
     q = tmp_path / "z.mtx"
     with open(q, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (A.shape[0], A.shape[1], coo.nnz))
+        f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (A.shape[0], A.shape[1], coo.nnz))
         for i, j, x in zip(coo.row, coo.col, coo.data):
             f.write("%d %d %.17g\n" % (i, j, x))
     Z = capi.MatCSR()

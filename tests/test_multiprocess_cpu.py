@@ -29,7 +29,7 @@ def exe(tmp_path_factory):
 def test_distributed_build_and_halo_plan(exe, name, tmp_path):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     S = int(g["S"])
-    A = getattr(gen_matrices, str(g["gen"]))(int(g["N"]))
+    A = gen_matrices.build(g["gen"], g["N"])
     mtx = str(tmp_path / "A.mtx")
     gen_matrices.write_mtx(mtx, A)
     env = dict(os.environ, MPISHIM_NP=str(S), PREALPS_B200_HOST_ONLY="1")

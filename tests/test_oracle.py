@@ -11,7 +11,7 @@ from conftest import GOLDEN, golden_cases
 
 def _case(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    A = getattr(gen_matrices, str(g["gen"]))(int(g["N"]))
+    A = gen_matrices.build(g["gen"], g["N"])
     return g, A
 
 
@@ -45,7 +45,12 @@ def test_rhs_and_ecg_history(name):
     g, A = _case(name)
     S, t = int(g["S"]), int(g["t"])
     P = restate.Partitioned(A, S)
-    out = restate.ecg_solve(P, t, float(g["tol"]), ortho=int(g["ortho"]))
+    adapt = "bs_red" in g.files and int(g["bs_red"]) == 1
+    if adapt:
+        out = restate.ecg_solve_adapt(P, t, float(g["tol"]))
+        assert np.array_equal(out["bs_hist"], g["bs_hist"])  # same reductions at the same iterations
+    else:
+        out = restate.ecg_solve(P, t, float(g["tol"]), ortho=int(g["ortho"]))
     for r in range(S):
         assert np.array_equal(out["rhs"][r], g["r%d_rhs" % r])  # glibc rand() stream, bit-exact
     assert out["iter"] == int(g["iter"])
@@ -53,9 +58,10 @@ def test_rhs_and_ecg_history(name):
     assert len(out["res_hist"]) == len(ref)
     # Orthodir amplifies rounding differences between two exact block solvers (SuperLU here, the shim
     # Cholesky in the golden run) up to ~1e-8 relative at the last iteration (measured: 1.0e-8 worst case)
-    assert np.allclose(out["res_hist"], ref, rtol=1e-7, atol=0)
+    # (the elasticity operators with ADAPT_BS: 1.9e-6 at the last iteration, numpy SVD vs the reference's dgesvd + dormqr)
+    assert np.allclose(out["res_hist"], ref, rtol=1e-5 if adapt else 1e-7, atol=0)
     assert np.allclose(out["res_hist"][:8], ref[:8], rtol=1e-10, atol=0)
     assert abs(out["normb"] - float(g["normb"])) <= 1e-14 * float(g["normb"])
     sol_ref = np.concatenate([g["r%d_sol" % r] for r in range(S)])
-    assert np.linalg.norm(out["sol"] - sol_ref) <= 1e-9 * np.linalg.norm(sol_ref)
+    assert np.linalg.norm(out["sol"] - sol_ref) <= (1e-7 if adapt else 1e-9) * np.linalg.norm(sol_ref)
     assert out["true_relres"] < 10 * float(g["tol"])
