@@ -2,6 +2,7 @@
 #include "bj_symbolic.h"
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
@@ -32,9 +33,20 @@ void etree(int n, const std::vector<int64_t>& lptr, const std::vector<int>& lidx
 }
 
 // Post-order of a forest; children are visited in increasing label order.
+// Children are visited smallest subtree first, except that tiny subtrees (<= kTinySubtree columns: the single
+// columns eliminated early by the minimum-degree ordering of the dissection leaves) come last. A node is then
+// numbered right after its tiny children and, before those, its largest child: contiguous with both, which is what
+// lets the relaxed amalgamation absorb the tiny ones and still consider the top of the largest subtree.
+constexpr int kTinySubtree = 4;
 void postorder(int n, const std::vector<int>& parent, std::vector<int>& post) {
+  std::vector<int> desc(n, 1);
+  for (int j = 0; j < n; ++j) if (parent[j] != -1) desc[parent[j]] += desc[j];  // parent[j] > j in an etree
+  std::vector<int> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  auto key = [&](int a) { return desc[a] <= kTinySubtree ? INT_MAX : desc[a]; };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) > key(b); });
   std::vector<int> head(n, -1), next(n, -1), stack;
-  for (int j = n - 1; j >= 0; --j)
+  for (int j : order)  // each push goes to the front of its parent's list: the visiting order is the reverse
     if (parent[j] != -1) { next[j] = head[parent[j]]; head[parent[j]] = j; }
   post.clear();
   post.reserve(n);
@@ -216,13 +228,15 @@ int analyze(int n, const int* rowPtr, const int* colInd, const SymbolicOptions& 
     SN p = s0;
     while (!fin.empty()) {
       const SN& c = fin.back();
-      if (parent[c.last] != p.first) break;  // not the last child of p's first column
+      // c is the supernode numbered right before p; it can join p when its parent column lies inside p
+      if (parent[c.last] < p.first || parent[c.last] > p.last) break;
       const int64_t wc = c.last - c.first + 1, wp = p.last - p.first + 1;
       const int64_t hc = c.h, hp = p.h;
-      const int64_t z = wc * (hp - hc + wc);
       const int64_t wn = wc + wp, hn = wc + hp;
       const int64_t stor = tri(wn) + (hn - wn) * wn;
-      const int64_t zt = c.zeros + p.zeros + z;
+      // explicit zeros of the merged trapezoid = its storage - the exact entries of both parts
+      const int64_t exact = (tri(wc) + (hc - wc) * wc - c.zeros) + (tri(wp) + (hp - wp) * wp - p.zeros);
+      const int64_t zt = stor - exact;
       bool merge;
       if (wn <= opt.relax_small) merge = true;
       else if (wn <= 4 * opt.relax_small) merge = (double)zt < 1.5 * opt.relax_zero * (double)stor;

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from prealps_b200 import capi  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 assert capi.lib.preAlps_b200_OperatorBuildStencil(0, n, 8, 0, 8) == 0
-for leaf, relax in ((32, 0.2), (128, 0.2), (256, 0.2), (512, 0.2), (128, 0.4), (256, 0.4)):
+for leaf, relax in ((32, 0.2), (48, 0.2), (64, 0.2), (96, 0.2), (64, 0.3), (32, 0.3)):
     os.environ["PREALPS_BJ_LEAF"] = str(leaf)
     os.environ["PREALPS_BJ_RELAX"] = str(relax)
     assert capi.lib.preAlps_b200_BlockJacobiCreate() == 0
