@@ -42,8 +42,9 @@ struct BwdPanel {      // one 32-row slice of M_s^T
   int pad_;
 };
 
-constexpr int kTinyS = 16, kTinyM = 32;  // ... shorter ones get a half / a quarter of the buffer: 2x / 4x more warps per SM
-constexpr int kTinyK = 64;  // panels up to this many steps are staged whole into shared memory
+constexpr int kTinyS = 16;  // ... and the very short ones get half of the buffer, 2x more warps per SM
+constexpr int kTinyK = 32;  // panels up to this many steps are staged whole into shared memory (64 was 3 % slower:
+                            // 20 KB of landing buffer per warp leaves 8 warps per SM)
 
 constexpr int kChunkMinKB = 128;            // shortest slice (k-blocks of 4 steps) a CTA gets when a long panel is cut across CTAs
 constexpr int kTinyFold = 512;              // fewer short panels than this at a level: no separate launch for them
@@ -82,7 +83,6 @@ struct pcu_bj {
   // panels with klen <= kTinyK at the end of each level's (klen-descending) list go to the tiny-panel kernel
   std::vector<int> fwd_tiny0, fwd_tinyn, bwd_tiny0, bwd_tinyn;
   std::vector<int> fwd_tinys, bwd_tinys;  // of those, the last *_tinys panels have klen <= kTinyS
-  std::vector<int> fwd_tinym, bwd_tinym;  // ... and the last *_tinym panels (a superset) have klen <= kTinyM
   // device: assembly of the forward right-hand side
   int* perm = nullptr;             // perm[forest col] = local row of the m x t block
   int* rows = nullptr;             // forest row index of every supernode row (gather index of the backward sweep)

@@ -537,11 +537,10 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   bj->fwd_tiny0.assign(nlev, 0); bj->fwd_tinyn.assign(nlev, 0);
   bj->bwd_tiny0.assign(nlev, 0); bj->bwd_tinyn.assign(nlev, 0);
   bj->fwd_tinys.assign(nlev, 0); bj->bwd_tinys.assign(nlev, 0);
-  bj->fwd_tinym.assign(nlev, 0); bj->bwd_tinym.assign(nlev, 0);
   const bool use_tiny = getenv("PREALPS_BJ_NOTINY") == nullptr;
   const bool use_chunks = getenv("PREALPS_BJ_NOCHUNK") == nullptr;
   auto make_units = [&](std::vector<int>& klen_of, int first, int count_all, std::vector<WorkUnit>& units, int* tiny0,
-                        int* tinyn, int* tinys, int* tinym) {
+                        int* tinyn, int* tinys) {
     int count = count_all;
     if (use_tiny) while (count > 0 && klen_of[first + count - 1] <= kTinyK) --count;
     // a handful of short panels next to longer ones ride along in the main launch (one warp each) instead of
@@ -552,9 +551,6 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     int cs = count_all;
     while (cs > count && klen_of[first + cs - 1] <= kTinyS) --cs;
     *tinys = count_all - cs;
-    int cm = count_all;
-    while (cm > count && klen_of[first + cm - 1] <= kTinyM) --cm;
-    *tinym = count_all - cm;
     // panels [first, first+count) are already sorted by klen descending
     int i = 0;
     int slots = 0, ctrs = 0;
@@ -614,7 +610,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     }
     kl.resize(fp.size());
     for (size_t i = f0; i < fp.size(); ++i) kl[i] = fp[i].klen;
-    make_units(kl, f0, (int)fp.size() - f0, fu, &bj->fwd_tiny0[l], &bj->fwd_tinyn[l], &bj->fwd_tinys[l], &bj->fwd_tinym[l]);
+    make_units(kl, f0, (int)fp.size() - f0, fu, &bj->fwd_tiny0[l], &bj->fwd_tinyn[l], &bj->fwd_tinys[l]);
     bj->fwd_unit_ptr[l + 1] = (int)fu.size();
     // backward
     lst.clear();
@@ -638,7 +634,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     }
     kl.assign(bp.size(), 0);
     for (size_t i = b0; i < bp.size(); ++i) kl[i] = bp[i].klen;
-    make_units(kl, b0, (int)bp.size() - b0, bu, &bj->bwd_tiny0[l], &bj->bwd_tinyn[l], &bj->bwd_tinys[l], &bj->bwd_tinym[l]);
+    make_units(kl, b0, (int)bp.size() - b0, bu, &bj->bwd_tiny0[l], &bj->bwd_tinyn[l], &bj->bwd_tinys[l]);
     bj->bwd_unit_ptr[l + 1] = (int)bu.size();
   }
   bj->fwd_doubles = fdoubles;

@@ -442,14 +442,13 @@ void launch_tiny_one(int first, int count, cudaStream_t st, const SweepArgs& a) 
   sweep_tiny_kernel<T, FWD, KMAX, WARPS><<<(count + WARPS - 1) / WARPS, WARPS * 32, bytes, st>>>(a, first, count);
 }
 
-// panels [first, first + count) are sorted by length: the last `nmed` have klen <= kTinyM, the last `nshort` of
-// those klen <= kTinyS; each class gets a landing buffer of its own size (more resident warps for shorter panels)
+// panels [first, first + count) are sorted by length, the last `nshort` ones have klen <= kTinyS: each class gets a
+// landing buffer of its own size (more resident warps for the shorter panels)
 template <int T, bool FWD>
-void launch_tiny(int first, int count, int nshort, int nmed, cudaStream_t st, const SweepArgs& a) {
-  const int nlong = count - nmed, nmid = nmed - nshort;
+void launch_tiny(int first, int count, int nshort, cudaStream_t st, const SweepArgs& a) {
+  const int nlong = count - nshort;
   if (nlong > 0) launch_tiny_one<T, FWD, kTinyK, 4>(first, nlong, st, a);
-  if (nmid > 0) launch_tiny_one<T, FWD, kTinyM, 4>(first + nlong, nmid, st, a);
-  if (nshort > 0) launch_tiny_one<T, FWD, kTinyS, 8>(first + nlong + nmid, nshort, st, a);
+  if (nshort > 0) launch_tiny_one<T, FWD, kTinyS, 8>(first + nlong, nshort, st, a);
 }
 
 template <int T, bool FWD>
@@ -522,10 +521,10 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       PCU_LAUNCH_CHECK(c);
     }
     if (bj->fwd_tinyn[l] > 0) {
-      prof.mark("fwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->fwd_tinyn[l]) + "/" + std::to_string(bj->fwd_tinym[l]) + "/" + std::to_string(bj->fwd_tinys[l]), 0.0);
+      prof.mark("fwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->fwd_tinyn[l]) + "/" + std::to_string(bj->fwd_tinys[l]), 0.0);
       a.panels = bj->fwd_panels;
       a.data = bj->fwd_data;
-      launch_tiny<T, true>(bj->fwd_tiny0[l], bj->fwd_tinyn[l], bj->fwd_tinys[l], bj->fwd_tinym[l], st, a);
+      launch_tiny<T, true>(bj->fwd_tiny0[l], bj->fwd_tinyn[l], bj->fwd_tinys[l], st, a);
       c->launches++;
       PCU_LAUNCH_CHECK(c);
     }
@@ -541,10 +540,10 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       PCU_LAUNCH_CHECK(c);
     }
     if (bj->bwd_tinyn[l] > 0) {
-      prof.mark("bwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->bwd_tinyn[l]) + "/" + std::to_string(bj->bwd_tinym[l]) + "/" + std::to_string(bj->bwd_tinys[l]), 0.0);
+      prof.mark("bwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->bwd_tinyn[l]) + "/" + std::to_string(bj->bwd_tinys[l]), 0.0);
       a.panels = bj->bwd_panels;
       a.data = bj->bwd_data;
-      launch_tiny<T, false>(bj->bwd_tiny0[l], bj->bwd_tinyn[l], bj->bwd_tinys[l], bj->bwd_tinym[l], st, a);
+      launch_tiny<T, false>(bj->bwd_tiny0[l], bj->bwd_tinyn[l], bj->bwd_tinys[l], st, a);
       c->launches++;
       PCU_LAUNCH_CHECK(c);
     }
