@@ -126,6 +126,15 @@ def workload_config(args):
             "l2": "inputs larger than L2 (factor + blocks ~17 GB per pass); per-kernel timings flush L2 between repetitions"}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one block-Jacobi apply from the committed ncu capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes_per_apply"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,7 +261,7 @@ def main():
                 "kernel": "block-Jacobi apply = sweep_kernel/sweep_tiny_kernel<%d> over all levels, forward + backward "
                           "(one launch group per pcu_bj_apply)" % args.t,
                 "achieved": bj["achieved_gbs"], "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
-                "frac": bj["achieved_gbs"] / peak, "traffic": None,
+                "frac": bj["achieved_gbs"] / peak, "traffic": ncu_traffic(),
                 "frac_of_nominal_8TBs": bj["achieved_gbs"] / 8000.0,
                 "algorithmic_bytes_per_apply": bj["algorithmic_bytes"],
                 "achieved_counting_exact_nnzL_only": exact_bytes / (bj["ms"] * 1e-3) / 1e9,

@@ -267,23 +267,25 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
   }
   // lane owns, for every row group rg and column block nb: row 8*rg + lane/4, columns 8*nb + 2*(lane%4) + {0,1}
   if (u.split) {
-    for (int wv = 0; wv < kWarps; ++wv) {  // fixed-order combine over the warps
-      if (warp == wv) {
+    // fixed-order combine over the warps: every warp parks its partial sums in its own (now idle) tile buffer,
+    // then each thread adds the 8 partials of one or more entries in warp order
 #pragma unroll
-        for (int rg = 0; rg < 4; ++rg)
+    for (int rg = 0; rg < 4; ++rg)
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb)
+      for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = 8 * nb + 2 * lk + e;
-              if (col < T) {
-                double* dst = red + (8 * rg + lr) * T + col;
-                if (wv == 0) *dst = acc[rg][nb][e]; else *dst += acc[rg][nb][e];
-              }
-            }
-      }
-      __syncthreads();
+        for (int e = 0; e < 2; ++e) {
+          const int col = 8 * nb + 2 * lk + e;
+          if (col < T) tile0[(8 * rg + lr) * T + col] = acc[rg][nb][e];
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * T; e += kThreads) {
+      double sum = smem[32 * T + e];
+#pragma unroll
+      for (int wv = 1; wv < kWarps; ++wv) sum += smem[32 * T + (size_t)wv * 2 * TILE + e];
+      red[e] = sum;
     }
+    __syncthreads();
     if (warp != 0) return;
     if (u.split == 2) {
       // long panel cut across CTAs: publish this slice, the CTA that arrives last adds all slices in slice order
