@@ -25,6 +25,13 @@ using namespace pcu;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
+// Programmatic dependent launch: the kernels of one apply form a chain (assemble / forward / backward, level after
+// level). Each is launched with programmatic stream serialization, so its CTAs may start while the previous
+// kernel drains: they fetch what does not depend on it (work units, panel descriptors, the first panel data), then
+// wait here for the previous kernel to complete. Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- forward right-hand-side assembly: one group of G lanes per column
 template <int T>
 __global__ void __launch_bounds__(kThreads) assemble_kernel(const int* __restrict__ cols, int ncols,
@@ -38,6 +45,8 @@ __global__ void __launch_bounds__(kThreads) assemble_kernel(const int* __restric
   const int gid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / G);
   const int lig = threadIdx.x % G;
   const int ngroups = (int)((long long)gridDim.x * blockDim.x / G);
+  pdl_wait();
+  pdl_launch_dependents();
   for (int q = gid; q < ncols; q += ngroups) {
     const int c = cols[q];
     const double* src = B + (size_t)perm[c] * ldb;
@@ -235,10 +244,15 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
       m1 = m0;
     }
   };
+  // panel data does not depend on the previous kernel: in flight before the wait
   if (q0 < q1) {
-    stage(q0, tile0);
 #pragma unroll
     for (int u2 = 0; u2 < D; ++u2) issue(q0 + u2, ring0[u2], ring1[u2]);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (q0 < q1) {
+    stage(q0, tile0);
     int tix = 0;
     for (int tq = q0; tq < q1; tq += KB, ++tix) {
       const double* cur = tile0 + (size_t)(tix & 1) * TILE;
@@ -350,6 +364,8 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
     cp_async16(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128);
     cp_async16(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2);
   }
+  pdl_wait();   // the panel itself is static; the input rows come from the previous kernel
+  pdl_launch_dependents();
   if (T >= 2) {
     constexpr int CPR = (T >= 2) ? T / 2 : 1;
     const int chunks = klen * CPR;
@@ -422,6 +438,23 @@ int ensure_work(pcu_bj* bj, int T) {
   return 0;
 }
 
+// launch with programmatic stream serialization (see pdl_wait); PREALPS_BJ_NOPDL=1 falls back to plain launches
+template <typename... KArgs, typename... Args>
+void launch_chain(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  static const bool pdl = getenv("PREALPS_BJ_NOPDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int T, bool FWD, int D, bool NOALLOC, int OCC>
 void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
   constexpr int bytes = (32 * T + kWarps * 2 * Tile<T>::KT * T) * (int)sizeof(double);
@@ -430,7 +463,7 @@ void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
     cudaFuncSetAttribute(sweep_kernel<T, FWD, D, NOALLOC, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     configured = true;
   }
-  sweep_kernel<T, FWD, D, NOALLOC, OCC><<<nu, kThreads, bytes, st>>>(a);
+  launch_chain(sweep_kernel<T, FWD, D, NOALLOC, OCC>, nu, kThreads, bytes, st, a);
 }
 
 template <int T, bool FWD, int KMAX, int WARPS>
@@ -441,7 +474,7 @@ void launch_tiny_one(int first, int count, cudaStream_t st, const SweepArgs& a) 
     cudaFuncSetAttribute(sweep_tiny_kernel<T, FWD, KMAX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     configured = true;
   }
-  sweep_tiny_kernel<T, FWD, KMAX, WARPS><<<(count + WARPS - 1) / WARPS, WARPS * 32, bytes, st>>>(a, first, count);
+  launch_chain(sweep_tiny_kernel<T, FWD, KMAX, WARPS>, (count + WARPS - 1) / WARPS, WARPS * 32, bytes, st, a, first, count);
 }
 
 // panels [first, first + count) are sorted by length, the last `nshort` ones have klen <= kTinyS: each class gets a
@@ -509,8 +542,8 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
     if (ncols > 0) {
       prof.mark("asm L" + std::to_string(l) + " cols=" + std::to_string(ncols), 3.0 * ncols * T * 8);
       const int grid = stream_grid(c, (long long)ncols * G, kThreads, 8);
-      assemble_kernel<T><<<grid, kThreads, 0, st>>>(bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t, bj->perm,
-                                                   bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
+      launch_chain(assemble_kernel<T>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t, bj->perm,
+                   bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
       PCU_LAUNCH_CHECK(c);
     }
     const int nu = bj->fwd_unit_ptr[l + 1] - bj->fwd_unit_ptr[l];
