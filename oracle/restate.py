@@ -268,10 +268,11 @@ def ecg_solve_adapt(P, t, tol, max_iter=1000, rhs=None):
             "true_relres": np.linalg.norm(b - A @ sol) / np.linalg.norm(b), "rhs": rhs}
 
 
-def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None):
+def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None, rrqr=False):
     """_preAlps_ECGIterateOdir / Omin with the driver loop (ecg.c:98-171,223-271,289-530;
     test_ecg_prealps_op.c:203-223), NO_BS_RED.  Global arrays; reductions summed over ranks in rank order
-    like the oracle's MPI shim."""
+    like the oracle's MPI shim.  rrqr=True (Orthomin only) adds the ADAPT_BS branch of ecg.c:360-393 -- the
+    rank-revealing Cholesky QR of the new directions -- for the full-rank case."""
     S, rowPos, M = P.S, P.rowPos, P.Ap.shape[0]
     sizes = [rowPos[r + 1] - rowPos[r] for r in range(S)]
     if rhs is None:
@@ -357,6 +358,12 @@ def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None):
             Z = prec(R)                                                  # test_ecg_prealps_op.c:217
             b = gsum(lambda r: AP[sl[r]].T @ Z[sl[r]])                   # ecg.c:347-352
             Pk = Z - Pk @ b                                              # ecg.c:354-358
+            if rrqr:
+                C = gsum(lambda r: Pk[sl[r]].T @ Pk[sl[r]])              # ecg.c:366-372
+                Uf, piv, rank, info = sla.lapack.dpstrf(np.triu(C), lower=0, tol=-1.0)   # ecg.c:375
+                if rank < t:
+                    raise ValueError("rank drop: the reference's handling of this case is inconsistent")
+                Pk = sla.solve_triangular(np.triu(Uf), Pk[:, piv - 1].T, trans="T", lower=False).T  # ecg.c:380-383
         AP = A @ Pk
     sol = X.sum(axis=1)                                                  # ecg.c:674
     b = np.concatenate(rhs)

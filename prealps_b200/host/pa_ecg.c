@@ -190,8 +190,8 @@ int preAlps_ECGInitialize(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   if (size < ecg->enlFac)
     CPLM_Abort("Enlarging factor must be lower than the number of processors in the MPI communicator! size: %d ; enlarging factor: %d",
                size, ecg->enlFac);
-  if (ecg->bs_red == ADAPT_BS && ecg->ortho_alg != ORTHODIR)
-    CPLM_Abort("adaptive reduction of the search directions (-r 1) is implemented for ORTHODIR (-o 0) only in this build");
+  if (ecg->bs_red == ADAPT_BS && ecg->ortho_alg == ORTHODIR_FUSED)
+    CPLM_Abort("adaptive reduction of the search directions (-r 1) is not implemented for ORTHODIR_FUSED in this build");
   _preAlps_ECGMalloc(ecg);
   return _preAlps_ECGReset(ecg, rhs, rci_request);
 }
@@ -444,6 +444,66 @@ int _preAlps_ECGIterateOdir(preAlps_ECG_t* ecg, int* rci_request) {
   return 0;
 }
 
+/* Cholesky with complete (diagonal) pivoting of the symmetric n x n matrix A (column-major, full storage):
+ * A[piv, piv] = U^T U, stops at the first pivot <= tol; tol < 0 selects LAPACK's default n * eps * max(diag)
+ * (stands in for LAPACKE_dpstrf('U'), ref: ecg.c:375).  U is returned in the upper triangle of A. */
+static int h_pivoted_chol(int n, double* A, int lda, int* piv, double tol) {
+  double dmax = 0.0;
+  for (int i = 0; i < n; ++i) { piv[i] = i; if (A[i + (size_t)lda * i] > dmax) dmax = A[i + (size_t)lda * i]; }
+  if (tol < 0.0) tol = n * 1.1102230246251565e-16 * dmax;
+  for (int j = 0; j < n; ++j) {
+    int p = j;
+    for (int i = j + 1; i < n; ++i) if (A[i + (size_t)lda * i] > A[p + (size_t)lda * p]) p = i;
+    if (!(A[p + (size_t)lda * p] > tol)) return j;
+    if (p != j) {  /* symmetric swap of rows/columns j and p */
+      for (int k = 0; k < n; ++k) { double tmp = A[j + (size_t)lda * k]; A[j + (size_t)lda * k] = A[p + (size_t)lda * k]; A[p + (size_t)lda * k] = tmp; }
+      for (int k = 0; k < n; ++k) { double tmp = A[k + (size_t)lda * j]; A[k + (size_t)lda * j] = A[k + (size_t)lda * p]; A[k + (size_t)lda * p] = tmp; }
+      int ti = piv[j]; piv[j] = piv[p]; piv[p] = ti;
+    }
+    const double d = sqrt(A[j + (size_t)lda * j]);
+    A[j + (size_t)lda * j] = d;
+    for (int c = j + 1; c < n; ++c) A[j + (size_t)lda * c] /= d;
+    for (int c = j + 1; c < n; ++c)      /* trailing update (full symmetric storage) */
+      for (int r = j + 1; r < n; ++r) A[r + (size_t)lda * c] -= A[j + (size_t)lda * r] * A[j + (size_t)lda * c];
+  }
+  return n;
+}
+
+/* Orthomin with ADAPT_BS (ref: ecg.c:360-393): after P <- Z the new directions are orthonormalised by a
+ * rank-revealing Cholesky QR, P <- P[:, piv] U^-1 with P^T P [piv, piv] = U^T U.  With full rank -- the only case
+ * the reference handles consistently: once the rank drops it keeps computing P^T P on the stale column count
+ * (ecg.c:366 uses P's old info while the copy at ecg.c:357 moved nrhs columns) -- this is one more block pass;
+ * a rank drop aborts with a message. */
+static void omin_rrqr(preAlps_ECG_t* ecg, ecg_priv_t* p) {
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, T = p->t, ld = p->ld;
+  double t0 = pa_wtime();
+  pa_cuda_check(pcu_gram2(c, m, T, p->P, ld, p->P, ld, sm_G(p), NULL, 0, NULL, 0, NULL), "pcu_gram2");
+  ecg->gemm_t += pa_wtime() - t0;
+  pa_allreduce_dev(sm_G(p), T * T, &ecg->comm_t);
+  double C[32 * 32], Ui[32 * 32], Wneg[32 * 32];
+  int piv[32];
+  pa_cuda_check(pcu_d2h(c, C, sm_G(p), sizeof(double) * (size_t)T * T), "pcu_d2h");
+  for (int j = 0; j < T; ++j) for (int i = j + 1; i < T; ++i) C[i + (size_t)T * j] = C[j + (size_t)T * i];  /* 'U' triangle */
+  t0 = pa_wtime();
+  const int rank = h_pivoted_chol(T, C, T, piv, -1.0);
+  ecg->pstrf_t += pa_wtime() - t0;
+  if (rank < T)
+    CPLM_Abort("ADAPT_BS with ORTHOMIN: the new search directions lost rank (%d of %d); the reduction itself is not "
+               "implemented (the reference's own handling of this case is inconsistent, ecg.c:357-366)", rank, T);
+  t0 = pa_wtime();
+  h_triu_inv(T, C, T, Ui, T);
+  for (int i = 0; i < T * T; ++i) Wneg[i] = 0.0;
+  for (int j = 0; j < T; ++j) for (int k = 0; k <= j; ++k) Wneg[piv[k] + (size_t)T * j] = -Ui[k + (size_t)T * j];
+  pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  /* P_prev's buffer is unused by Orthomin: P W is formed there and the two buffers trade places */
+  pa_cuda_check(pcu_memset(c, p->Pp, 0, sizeof(double) * (size_t)m * ld), "pcu_memset");
+  pa_cuda_check(pcu_update_z(c, m, T, p->Pp, ld, p->P, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
+  double* old = p->P; p->P = p->Pp; p->Pp = old;
+  ecg->lapmt_t += pa_wtime() - t0;
+  ecg->bs = T;
+}
+
 int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
   ecg_priv_t* p = priv_of(ecg);
   pcu_ctx* c = pa_g.ctx;
@@ -462,6 +522,7 @@ int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
     ecg->gemm_t += pa_wtime() - t0;
     double* oldP = p->P;
     p->P = p->Z; p->Z = oldP;
+    if (p->adapt) omin_rrqr(ecg, p);
     refresh_shells(ecg, p);
     *rci_request = 0;
   }

@@ -46,7 +46,10 @@ def test_rhs_and_ecg_history(name):
     S, t = int(g["S"]), int(g["t"])
     P = restate.Partitioned(A, S)
     adapt = "bs_red" in g.files and int(g["bs_red"]) == 1
-    if adapt:
+    if adapt and int(g["ortho"]) == 1:
+        out = restate.ecg_solve(P, t, float(g["tol"]), ortho=1, rrqr=True)
+        assert np.all(g["bs_hist"] == t)  # the rank never drops
+    elif adapt:
         out = restate.ecg_solve_adapt(P, t, float(g["tol"]))
         assert np.array_equal(out["bs_hist"], g["bs_hist"])  # same reductions at the same iterations
     else:
