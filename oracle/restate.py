@@ -268,6 +268,89 @@ def ecg_solve_adapt(P, t, tol, max_iter=1000, rhs=None):
             "true_relres": np.linalg.norm(b - A @ sol) / np.linalg.norm(b), "rhs": rhs}
 
 
+def ecg_solve_fused_adapt(P, t, tol, max_iter=1000, rhs=None):
+    """_preAlps_ECGIterateOdirFused with bs_red = ADAPT_BS (ecg.c:532-658, reduction at :593-641) inside the loop of
+    test_ecg_bench_fused.c:245-259.  Same slot layout as ecg_solve_adapt; the Gram products are taken before the
+    normalisation by U = chol(AP^T P) and the residual test lags one iteration."""
+    import scipy.linalg as sla
+    S, rowPos, M = P.S, P.rowPos, P.Ap.shape[0]
+    sizes = [rowPos[r + 1] - rowPos[r] for r in range(S)]
+    if rhs is None:
+        rhs = driver_rhs(sizes)
+    sl = [slice(rowPos[r], rowPos[r + 1]) for r in range(S)]
+    lus = P.block_solvers()
+    A = P.Ap
+    nrhs = t
+
+    def gsum(f):
+        acc = f(0)
+        for r in range(1, S):
+            acc = acc + f(r)
+        return acc
+
+    def prec(B):
+        Z = np.empty_like(B)
+        for r in range(S):
+            Z[sl[r]] = lus[r].solve(B[sl[r]])
+        return Z
+
+    normb = np.sqrt(gsum(lambda r: float(np.sum(rhs[r] ** 2))))
+    R = np.zeros((M, nrhs))
+    for r in range(S):
+        R[sl[r], r % nrhs] = rhs[r]
+    X = np.zeros((M, nrhs))
+    V = np.zeros((M, 2 * nrhs)); AV = np.zeros((M, 2 * nrhs))
+    V[:, :nrhs] = prec(R)
+    bs, kbs = nrhs, 2 * nrhs
+    cut = tol * normb / np.sqrt(nrhs)
+    hist, bs_hist, it = [], [], 0
+    rsolve = lambda U, B: sla.solve_triangular(U, B.T, trans="T", lower=False).T   # B U^-1
+    while True:
+        tt = bs
+        AV[:, :tt] = A @ V[:, :tt]                                       # test_ecg_bench_fused.c:252
+        Z = prec(AV[:, :tt])                                             # :253
+        Pk, AP = V[:, :tt], AV[:, :tt]
+        alpha = gsum(lambda r: Pk[sl[r]].T @ R[sl[r]])                   # ecg.c:557 (tt x nrhs)
+        beta = gsum(lambda r: AV[sl[r], :kbs].T @ Z[sl[r]])              # ecg.c:558 (kbs x tt)
+        mu = gsum(lambda r: AP[sl[r]].T @ Pk[sl[r]])                     # ecg.c:559
+        rtr = gsum(lambda r: R[sl[r]].T @ R[sl[r]])                      # ecg.c:560
+        res = np.sqrt(np.trace(rtr))
+        hist.append(res)
+        conv = res < tol * normb or it > max_iter                        # ecg.c:571
+        U = sla.cholesky(np.triu(mu) + np.triu(mu, 1).T, lower=False)    # ecg.c:577
+        Pk[:] = rsolve(U, Pk); AP[:] = rsolve(U, AP)                     # ecg.c:580-581
+        beta = rsolve(U, beta); Z = rsolve(U, Z)                         # ecg.c:582-583
+        alpha = sla.solve_triangular(U, alpha, trans="T", lower=False)   # ecg.c:584
+        beta[:tt] = sla.solve_triangular(U, beta[:tt], trans="T", lower=False)   # ecg.c:586 (first t rows)
+        Z = Z - V[:, :kbs] @ beta                                        # ecg.c:590
+        Us, sv, _ = np.linalg.svd(alpha, full_matrices=True)             # ecg.c:600
+        t1 = 0
+        for sgm in sv[:tt]:
+            if sgm > cut:
+                t1 += 1
+            else:
+                break
+        if 0 < t1 < nrhs and t1 < tt:                                    # ecg.c:609
+            Q = Us
+            alpha = (Q.T @ alpha)[:t1]
+            Pk[:] = Pk @ Q; AP[:] = AP @ Q                               # ecg.c:617-620
+            Z = (Z @ Q)[:, :t1]                                          # ecg.c:621-622,631
+            bs, kbs = t1, tt + nrhs                                      # ecg.c:635-636
+        bs_hist.append(bs)                                               # what the driver sees after Iterate
+        X = X + V[:, :bs] @ alpha                                        # ecg.c:644-645
+        R = R - AV[:, :bs] @ alpha
+        it += 1
+        V[:, nrhs:nrhs + bs] = V[:, :bs]                                 # ecg.c:651-653
+        AV[:, nrhs:nrhs + bs] = AV[:, :bs]
+        V[:, :bs] = Z
+        if conv:
+            break
+    sol = X.sum(axis=1)
+    b = np.concatenate(rhs)
+    return {"iter": it, "res_hist": np.array(hist), "bs_hist": np.array(bs_hist), "sol": sol, "normb": normb,
+            "true_relres": np.linalg.norm(b - A @ sol) / np.linalg.norm(b), "rhs": rhs}
+
+
 def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None, rrqr=False):
     """_preAlps_ECGIterateOdir / Omin with the driver loop (ecg.c:98-171,223-271,289-530;
     test_ecg_prealps_op.c:203-223), NO_BS_RED.  Global arrays; reductions summed over ranks in rank order

@@ -33,7 +33,8 @@
 typedef struct {
   preAlps_ECG_t* owner;
   int m, t, ld;
-  double* buf[7];       /* P, Pprev, AP, APprev, Z, R, X (roles rotate, see rotate()) */
+  double* buf[8];       /* P, Pprev, AP, APprev, Z, R, X (roles rotate) + a scratch block (ADAPT_BS with ORTHODIR_FUSED) */
+  int nbuf;
   double *P, *Pp, *AP, *APp, *Z, *R, *X;
   double* small;        /* G | Gpr | U | alpha | beta1 | beta2 | rr_local | rr_glob */
   double* rhs_dev;
@@ -44,6 +45,7 @@ typedef struct {
   /* ADAPT_BS: after the first reduction the buffers stop rotating (slot0 = P/AP, slot1 = Pp/APp) */
   int adapt, fixed;
   int tprev;            /* columns of slot1 that still take part in the A-orthogonalisation (kbs - t) */
+  double* scratch;      /* 8th block */
 } ecg_priv_t;
 
 #define MAX_SOLVERS 16
@@ -102,11 +104,12 @@ int _preAlps_ECGMalloc(preAlps_ECG_t* ecg) {
   const size_t blk = (size_t)m * p->ld;
   const size_t smalls = 8 * (size_t)t * t + 16;
   /* one pool, like the reference's mkl_calloc(7mt + 3t^2) (ref: ecg.c:58-62), but in HBM */
-  ecg->work = (double*)pcu_malloc(c, sizeof(double) * (7 * blk + smalls + 8));
+  p->nbuf = (ecg->bs_red == ADAPT_BS && ecg->ortho_alg == ORTHODIR_FUSED) ? 8 : 7;
+  ecg->work = (double*)pcu_malloc(c, sizeof(double) * (p->nbuf * blk + smalls + 8));
   if (!ecg->work) CPLM_Abort("device allocation of the ECG pool failed: %s", pcu_last_error());
-  pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * (7 * blk + smalls + 8)), "pcu_memset");
-  for (int i = 0; i < 7; ++i) p->buf[i] = ecg->work + (size_t)i * blk;
-  p->small = ecg->work + 7 * blk;
+  pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * (p->nbuf * blk + smalls + 8)), "pcu_memset");
+  for (int i = 0; i < p->nbuf; ++i) p->buf[i] = ecg->work + (size_t)i * blk;
+  p->small = ecg->work + p->nbuf * blk;
   p->rhs_dev = (double*)pcu_malloc(c, sizeof(double) * (size_t)(m > 0 ? m : 1));
   p->col_of_row = (int*)pcu_malloc(c, sizeof(int) * (size_t)(m > 0 ? m : 1));
   p->status_dev = (int*)pcu_malloc(c, sizeof(int) * 4);
@@ -135,7 +138,8 @@ int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   const size_t blk = (size_t)m * p->ld;
   p->P = p->buf[0]; p->Pp = p->buf[1]; p->AP = p->buf[2]; p->APp = p->buf[3];
   p->Z = p->buf[4]; p->R = p->buf[5]; p->X = p->buf[6];
-  pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * 7 * blk), "pcu_memset");
+  p->scratch = p->nbuf > 7 ? p->buf[7] : NULL;
+  pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * p->nbuf * blk), "pcu_memset");
   /* ||b||: per-subdomain sums in row order, then summed over subdomains/processes (ref: ecg.c:143-155) */
   double nb = 0.0;
   int* cor = (int*)pa_xmalloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
@@ -190,8 +194,6 @@ int preAlps_ECGInitialize(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   if (size < ecg->enlFac)
     CPLM_Abort("Enlarging factor must be lower than the number of processors in the MPI communicator! size: %d ; enlarging factor: %d",
                size, ecg->enlFac);
-  if (ecg->bs_red == ADAPT_BS && ecg->ortho_alg == ORTHODIR_FUSED)
-    CPLM_Abort("adaptive reduction of the search directions (-r 1) is not implemented for ORTHODIR_FUSED in this build");
   _preAlps_ECGMalloc(ecg);
   return _preAlps_ECGReset(ecg, rhs, rci_request);
 }
@@ -529,6 +531,127 @@ int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
   return 0;
 }
 
+/* scratch <- block * (-Wneg) with Wneg T x T on the device; the block and the scratch buffer then trade places */
+static void right_multiply(ecg_priv_t* p, double** block, const double* Wneg_dev) {
+  pcu_ctx* c = pa_g.ctx;
+  pa_cuda_check(pcu_memset(c, p->scratch, 0, sizeof(double) * (size_t)p->m * p->ld), "pcu_memset");
+  pa_cuda_check(pcu_update_z(c, p->m, p->t, p->scratch, p->ld, *block, p->ld, p->t, Wneg_dev, NULL, 0, 0, NULL), "pcu_update_z");
+  double* old = *block; *block = p->scratch; p->scratch = old;
+}
+
+/* ORTHODIR_FUSED with ADAPT_BS (ref: ecg.c:532-658, reduction at :593-641). Same slot layout and zero/identity
+ * padding as adapt_half_step. The five Gram products are taken on the un-normalised blocks at the full width T and
+ * reduced together; the t x t algebra (Cholesky, the scalings of ecg.c:580-587, SVD) runs on the host; with
+ * W = U^-1 Q (Q = I when nothing is dropped):
+ *   slot0 <- slot0 diag(W, I);  A slot0 likewise;
+ *   Z <- Z W - slot0 [Q^T b1p Q; b1h Q] - slot1 [b2 Q]      (b1p/b1h: rows of beta for the live / the discarded
+ *                                                            directions, b2: previous directions, all scaled as ecg.c:582,586)
+ *   X += slot0 [Q^T alpha (first t1 rows); 0];  R -= A slot0 [..];  copies of ecg.c:651-653 on bs columns.
+ * Until the first reduction an iteration that drops nothing takes the NO_BS_RED path. Returns 1 if that path
+ * must be taken by the caller. */
+static int fused_adapt_step(preAlps_ECG_t* ecg, ecg_priv_t* p, const double* H) {
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, T = p->t, ld = p->ld, bs = ecg->bs;
+  const double* alpha_f = H;
+  const double* beta1_f = H + (size_t)T * T;
+  const double* beta2_f = H + 2 * (size_t)T * T;
+  double mu[32 * 32], Ui[32 * 32], alpha[32 * 32], Q[32 * 32], rows[32 * 32], sv[32];
+  for (int i = 0; i < T * T; ++i) mu[i] = H[3 * (size_t)T * T + i];
+  double t0 = pa_wtime();
+  h_chol_upper(bs, mu, T);
+  ecg->potrf_t += pa_wtime() - t0;
+  h_triu_inv(bs, mu, T, Ui, bs);
+  for (int j = 0; j < T; ++j)
+    for (int i = 0; i < bs; ++i) {
+      double v = 0.0;
+      for (int k = 0; k <= i; ++k) v += Ui[k + (size_t)bs * i] * alpha_f[k + (size_t)T * j];
+      alpha[i + (size_t)bs * j] = v;
+    }
+  t0 = pa_wtime();
+  h_left_svd(bs, T, alpha, bs, sv, Q, rows);
+  ecg->gesvd_t += pa_wtime() - t0;
+  const double cut = ecg->tol * ecg->normb / sqrt((double)T);
+  int t1 = 0;
+  for (int i = 0; i < bs; ++i) { if (sv[i] > cut) t1++; else break; }
+  const int reduce = (t1 > 0 && t1 < T && t1 < bs);
+  if (!reduce && !p->fixed) return 1;
+  if (!reduce) { for (int i = 0; i < bs * bs; ++i) Q[i] = 0.0; for (int i = 0; i < bs; ++i) Q[i + (size_t)bs * i] = 1.0; }
+  /* B1 = beta1[:, :bs] U^-1 (all T rows), first bs rows also U^-T from the left; B2 = beta2[:, :bs] U^-1 */
+  double B1[32 * 32], B2[32 * 32], tmp[32 * 32];
+  for (int j = 0; j < bs; ++j)
+    for (int i = 0; i < T; ++i) {
+      double v1 = 0.0, v2 = 0.0;
+      for (int k = 0; k <= j; ++k) { v1 += beta1_f[i + (size_t)T * k] * Ui[k + (size_t)bs * j]; v2 += beta2_f[i + (size_t)T * k] * Ui[k + (size_t)bs * j]; }
+      B1[i + (size_t)T * j] = v1; B2[i + (size_t)T * j] = v2;
+    }
+  for (int j = 0; j < bs; ++j) {
+    for (int i = 0; i < bs; ++i) {
+      double v = 0.0;
+      for (int k = 0; k <= i; ++k) v += Ui[k + (size_t)bs * i] * B1[k + (size_t)T * j];
+      tmp[i] = v;
+    }
+    for (int i = 0; i < bs; ++i) B1[i + (size_t)T * j] = tmp[i];
+  }
+  /* Wneg = -diag(U^-1 Q, I); Bf1 = [Q^T B1p Q; B1h Q]; Bf2 = B2 Q; Af = [Q^T alpha (keep rows); 0] -- T x T */
+  double Wneg[32 * 32], Bf1[32 * 32], Bf2[32 * 32], Af[32 * 32];
+  for (int i = 0; i < T * T; ++i) { Wneg[i] = 0.0; Bf1[i] = 0.0; Bf2[i] = 0.0; Af[i] = 0.0; }
+  for (int j = 0; j < T; ++j) Wneg[j + (size_t)T * j] = -1.0;
+  for (int j = 0; j < bs; ++j)
+    for (int i = 0; i < bs; ++i) {
+      double v = 0.0;
+      for (int k = i; k < bs; ++k) v += Ui[i + (size_t)bs * k] * Q[k + (size_t)bs * j];
+      Wneg[i + (size_t)T * j] = -v;
+    }
+  for (int j = 0; j < bs; ++j)       /* tmp2 = B1 Q and B2 Q (T x bs) */
+    for (int i = 0; i < T; ++i) {
+      double v1 = 0.0, v2 = 0.0;
+      for (int k = 0; k < bs; ++k) { v1 += B1[i + (size_t)T * k] * Q[k + (size_t)bs * j]; v2 += B2[i + (size_t)T * k] * Q[k + (size_t)bs * j]; }
+      Bf1[i + (size_t)T * j] = v1; Bf2[i + (size_t)T * j] = v2;
+    }
+  for (int j = 0; j < bs; ++j) {     /* first bs rows of Bf1: Q^T from the left */
+    for (int i = 0; i < bs; ++i) {
+      double v = 0.0;
+      for (int k = 0; k < bs; ++k) v += Q[k + (size_t)bs * i] * Bf1[k + (size_t)T * j];
+      tmp[i] = v;
+    }
+    for (int i = 0; i < bs; ++i) Bf1[i + (size_t)T * j] = tmp[i];
+  }
+  const int keep = reduce ? t1 : bs;
+  for (int j = 0; j < T; ++j)
+    for (int i = 0; i < keep; ++i) Af[i + (size_t)T * j] = reduce ? rows[(size_t)i * T + j] : alpha[i + (size_t)bs * j];
+  pa_cuda_check(pcu_h2d(c, fu_mu(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  pa_cuda_check(pcu_h2d(c, fu_beta1(p), Bf1, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  pa_cuda_check(pcu_h2d(c, fu_beta2(p), Bf2, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  pa_cuda_check(pcu_h2d(c, fu_alpha(p), Af, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  t0 = pa_wtime();
+  right_multiply(p, &p->P, fu_mu(p));
+  right_multiply(p, &p->AP, fu_mu(p));
+  right_multiply(p, &p->Z, fu_mu(p));
+  ecg->ormqr_t += pa_wtime() - t0;
+  t0 = pa_wtime();
+  pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->P, ld, T, fu_beta1(p), p->Pp, ld, T, fu_beta2(p)), "pcu_update_z");
+  if (keep < T) pa_cuda_check(pcu_zero_cols(c, m, T - keep, p->Z + keep, ld), "pcu_zero_cols");
+  pa_cuda_check(pcu_update_xr(c, m, T, p->P, ld, p->AP, ld, fu_alpha(p), p->X, ld, p->R, ld, sm_rr(p)), "pcu_update_xr");
+  ecg->gemm_t += pa_wtime() - t0;
+  if (reduce) {
+    ecg->bs = t1;
+    ecg->kbs = bs + T;
+    p->tprev = bs;
+    p->fixed = 1;
+    pa_cuda_check(pcu_zero_cols(c, m, T - bs, p->Pp + bs, ld), "pcu_zero_cols");
+    pa_cuda_check(pcu_zero_cols(c, m, T - bs, p->APp + bs, ld), "pcu_zero_cols");
+  }
+  ecg->iter++;
+  p->have_rr = 1;
+  t0 = pa_wtime();
+  pa_cuda_check(pcu_copy_cols(c, m, ecg->bs, p->Pp, ld, p->P, ld), "pcu_copy_cols");
+  pa_cuda_check(pcu_copy_cols(c, m, ecg->bs, p->APp, ld, p->AP, ld), "pcu_copy_cols");
+  pa_cuda_check(pcu_copy_cols(c, m, ecg->bs, p->P, ld, p->Z, ld), "pcu_copy_cols");
+  ecg->copy_t += pa_wtime() - t0;
+  refresh_shells(ecg, p);
+  return 0;
+}
+
 /* ref: ecg.c:532-658.  One all-reduce per iteration: alpha = P^T R, beta = [AP^T Z; APprev^T Z], mu = AP^T P and
  * R^T R are formed from the un-normalised blocks, reduced together, and the normalisation by U = chol(mu) is
  * applied afterwards (P, AP, Z <- . U^-1; alpha <- U^-T alpha; beta1 <- U^-T beta1 U^-1; beta2 <- beta2 U^-1).
@@ -536,7 +659,7 @@ int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
 int _preAlps_ECGIterateOdirFused(preAlps_ECG_t* ecg, int* rci_request) {
   ecg_priv_t* p = priv_of(ecg);
   pcu_ctx* c = pa_g.ctx;
-  const int m = p->m, t = ecg->bs, ld = p->ld;
+  const int m = p->m, t = p->adapt ? p->t : ecg->bs, ld = p->ld;  /* ADAPT_BS: full width, zero-padded blocks */
   double t0 = pa_wtime();
   pa_cuda_check(pcu_gram2(c, m, t, p->P, ld, p->R, ld, fu_alpha(p), p->AP, ld, p->P, ld, fu_mu(p)), "pcu_gram2");
   pa_cuda_check(pcu_gram2(c, m, t, p->AP, ld, p->Z, ld, fu_beta1(p), p->APp, ld, p->Z, ld, fu_beta2(p)), "pcu_gram2");
@@ -544,10 +667,17 @@ int _preAlps_ECGIterateOdirFused(preAlps_ECG_t* ecg, int* rci_request) {
   ecg->gemm_t += pa_wtime() - t0;
   pa_allreduce_dev(fu_alpha(p), 4 * p->t * p->t + 1, &ecg->comm_t);
   double rr = 0.0;
-  pa_cuda_check(pcu_d2h(c, &rr, fu_rr(p), sizeof(double)), "pcu_d2h");
+  double Hs[4 * 32 * 32 + 1];
+  if (p->adapt) {
+    pa_cuda_check(pcu_d2h(c, Hs, fu_alpha(p), sizeof(double) * (4 * (size_t)p->t * p->t + 1)), "pcu_d2h");
+    rr = Hs[4 * (size_t)p->t * p->t];
+  } else {
+    pa_cuda_check(pcu_d2h(c, &rr, fu_rr(p), sizeof(double)), "pcu_d2h");
+  }
   ecg->res = sqrt(rr);
   if (ecg->res < ecg->tol * ecg->normb || ecg->iter > ecg->maxIter) *rci_request = 1;
   else *rci_request = 0;
+  if (p->adapt && !fused_adapt_step(ecg, p, Hs)) return 0;
   t0 = pa_wtime();
   pa_cuda_check(pcu_fused_small(c, t, fu_mu(p), fu_beta1(p), fu_beta2(p), fu_U(p), p->status_dev), "pcu_fused_small");
   pa_cuda_check(pcu_right_solve(c, m, t, fu_mu(p), p->Z, ld), "pcu_right_solve");

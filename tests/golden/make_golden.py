@@ -36,6 +36,7 @@ CASES = [
     ("elasticity3d_766_s8_t8_odir_adapt", "elasticity3d", (7, 6, 6), 8, 8, 0, 1e-8, 1),
     ("elasticity3d_655_s4_t4_odir_adapt", "elasticity3d", (6, 5, 5), 4, 4, 0, 1e-8, 1),
     ("elasticity3d_655_s4_t4_omin_adapt", "elasticity3d", (6, 5, 5), 4, 4, 1, 1e-8, 1),
+    ("elasticity3d_766_s8_t8_fused_adapt", "elasticity3d", (7, 6, 6), 8, 8, 2, 1e-8, 1),
 ]
 
 

@@ -203,8 +203,10 @@ def test_driver_error_behaviour_matches_reference():
     assert "Enlarging factor must be lower than the number of processors" in out.stderr
 
 
-def test_unchanged_fused_bench_driver():
-    """examples/test_ecg_bench_fused.c of the reference, compiled unchanged: runs Orthodir and ORTHODIR_FUSED back to back"""
+@pytest.mark.parametrize("bs_red", [0, 1])
+def test_unchanged_fused_bench_driver(bs_red):
+    """examples/test_ecg_bench_fused.c of the reference, compiled unchanged: runs Orthodir and ORTHODIR_FUSED back to back
+    (-r 1: both with the adaptive reduction of the search directions)"""
     exe = os.path.join(ROOT, "prealps_b200", "bin", "test_ecg_bench_fused")
     if not os.path.exists(exe):
         pytest.skip("driver binary not built")
@@ -214,8 +216,8 @@ def test_unchanged_fused_bench_driver():
         mtx = os.path.join(d, "A.mtx")
         gen_matrices.write_mtx(mtx, A)
         env = dict(os.environ, MPISHIM_NP="8")
-        out = subprocess.run([exe, "-e", "8", "-m", mtx, "-r", "0", "-t", "1e-8"], env=env, capture_output=True, text=True,
-                             timeout=600)
+        out = subprocess.run([exe, "-e", "8", "-m", mtx, "-r", str(bs_red), "-t", "1e-8"], env=env, capture_output=True,
+                             text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     # this driver prints timings only (ref: test_ecg_bench_fused.c:300-334); both solves must have run to the end
     assert "=== ODIR ===" in out.stdout and "=== F-ODIR ===" in out.stdout

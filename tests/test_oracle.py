@@ -49,6 +49,9 @@ def test_rhs_and_ecg_history(name):
     if adapt and int(g["ortho"]) == 1:
         out = restate.ecg_solve(P, t, float(g["tol"]), ortho=1, rrqr=True)
         assert np.all(g["bs_hist"] == t)  # the rank never drops
+    elif adapt and int(g["ortho"]) == 2:
+        out = restate.ecg_solve_fused_adapt(P, t, float(g["tol"]))
+        assert np.array_equal(out["bs_hist"], g["bs_hist"])
     elif adapt:
         out = restate.ecg_solve_adapt(P, t, float(g["tol"]))
         assert np.array_equal(out["bs_hist"], g["bs_hist"])  # same reductions at the same iterations
