@@ -264,6 +264,7 @@ int pa_kway_parts(const CPLM_Mat_CSR_t* A, int S, int* parts) {
  * posB = exclusive prefix sums of the part sizes; perm[new] = old, parts in id order and the
  * original order kept inside a part. */
 void pa_parts_to_perm(int M, const int* parts, int S, int* posB, int* perm) {
+  if (S < 1) return;
   for (int s = 0; s <= S; ++s) posB[s] = 0;
   for (int i = 0; i < M; ++i) posB[parts[i] + 1]++;
   for (int s = 0; s < S; ++s) posB[s + 1] += posB[s];
