@@ -387,6 +387,11 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     else { for (int i = 0; i < nthr; ++i) pool.emplace_back(work, i); for (auto& th : pool) th.join(); }
   }
   for (int b = 0; b < nblk; ++b) PCU_CHECK(rc[b] == 0, "pcu_bj_create: symbolic analysis of block %d failed (%d)", b, rc[b]);
+  if (getenv("PREALPS_BJ_PROFILE")) {
+    double tmax = 0.0, tsum = 0.0;
+    for (auto& S : sym) { tmax = std::max(tmax, S.ordering_seconds); tsum += S.ordering_seconds; }
+    fprintf(stderr, "  analysis: METIS_NodeND max %.2f s, sum %.2f s over %d blocks\n", tmax, tsum, nblk);
+  }
 
   // ---------------------------------------------------------------- forest
   pcu_bj* bj = new pcu_bj();

@@ -2,6 +2,7 @@
 #include "bj_symbolic.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -131,8 +132,11 @@ int analyze(int n, const int* rowPtr, const int* colInd, const SymbolicOptions& 
   if (opt.use_metis && n >= 8 && xadj[n] > 0) {
     std::vector<int64_t> p64(n), ip64(n);
     int64_t nv = n;
+    const auto tm0 = std::chrono::steady_clock::now();
     int rc = METIS_NodeND(&nv, xadj.data(), adj.data(), nullptr, nullptr, p64.data(), ip64.data());
     if (rc != 1) return -3;
+    S->ordering_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tm0).count();
+    if (getenv("PREALPS_BJ_PROFILE")) fprintf(stderr, "  METIS_NodeND(n=%d): %.2f s\n", n, S->ordering_seconds);
     for (int i = 0; i < n; ++i) { mperm[i] = (int)p64[i]; miperm[i] = (int)ip64[i]; }
   } else {
     std::iota(mperm.begin(), mperm.end(), 0);

@@ -26,6 +26,7 @@ struct Symbolic {
   int nlevels = 0;
   std::vector<int> col2sn;        // n: supernode of each column
   int64_t nnzL_exact = 0;         // sum of exact column counts (no relaxation)
+  double ordering_seconds = 0.0;  // time spent in METIS_NodeND
   int64_t nnzL_stored = 0;        // sum over supernodes of w*(w+1)/2 + (h-w)*w (dense trapezoids)
   double flops = 0;               // sum of squared column counts of the stored structure
 };
