@@ -488,14 +488,9 @@ void launch_tiny(int first, int count, int nshort, cudaStream_t st, const SweepA
 
 template <int T, bool FWD>
 void launch_sweep(int nu, cudaStream_t st, const SweepArgs& a) {
-  const char* e = getenv("PREALPS_BJ_VARIANT");
-  const int variant = e ? atoi(e) : 0;
-  switch (variant) {
-    case 1: launch_one<T, FWD, (T <= 16 ? 8 : 4), true, 2>(nu, st, a); break;
-    case 2: launch_one<T, FWD, 4, false, 2>(nu, st, a); break;
-    case 3: launch_one<T, FWD, 2, true, 3>(nu, st, a); break;
-    default: launch_one<T, FWD, 4, true, 2>(nu, st, a); break;
-  }
+  // ring of 4 k-blocks per warp, streaming (no L1 allocation) panel loads, 2 CTAs per SM: the best of the
+  // combinations measured on B200 (deeper rings and 3 CTAs/SM spill; allocating loads are 2 % slower)
+  launch_one<T, FWD, 4, true, 2>(nu, st, a);
 }
 
 // PREALPS_BJ_PROFILE=1: per-launch CUDA-event timings of one apply, printed to stderr

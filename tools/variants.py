@@ -1,4 +1,5 @@
-"""tools/variants.py -- time the block-Jacobi apply for each PREALPS_BJ_VARIANT on the bench operator"""
+"""tools/variants.py -- time the block-Jacobi apply on the bench operator (Poisson n^3, `nsub` subdomains on this GPU):
+    python tools/variants.py [n = 128] [0] [nsub = 8]"""
 import ctypes as C
 import os
 import sys
