@@ -79,7 +79,8 @@ struct pcu_bj {
   pcu::WorkUnit* fwd_units = nullptr;
   pcu::WorkUnit* bwd_units = nullptr;
   std::vector<int> fwd_unit_ptr, bwd_unit_ptr;   // per level, nlevels+1
-  std::vector<double> fwd_lvl_bytes, bwd_lvl_bytes;  // panel bytes per level (profiling)
+  std::vector<double> fwd_lvl_bytes, bwd_lvl_bytes;    // panel bytes per level (profiling)
+  std::vector<double> fwd_tiny_bytes, bwd_tiny_bytes;  // of which in the tiny-panel launches
   // panels with klen <= kTinyK at the end of each level's (klen-descending) list go to the tiny-panel kernel
   std::vector<int> fwd_tiny0, fwd_tinyn, bwd_tiny0, bwd_tinyn;
   std::vector<int> fwd_tinys, bwd_tinys;  // of those, the last *_tinys panels have klen <= kTinyS

@@ -535,6 +535,8 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   bj->fwd_unit_ptr.assign(nlev + 1, 0);
   bj->fwd_lvl_bytes.assign(nlev, 0.0);
   bj->bwd_lvl_bytes.assign(nlev, 0.0);
+  bj->fwd_tiny_bytes.assign(nlev, 0.0);
+  bj->bwd_tiny_bytes.assign(nlev, 0.0);
   bj->bwd_unit_ptr.assign(nlev + 1, 0);
   std::vector<std::vector<PackTask>> pk_f(nlev), pk_b(nlev);
   long long fdoubles = 0, bdoubles = 0;
@@ -616,6 +618,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     kl.resize(fp.size());
     for (size_t i = f0; i < fp.size(); ++i) kl[i] = fp[i].klen;
     make_units(kl, f0, (int)fp.size() - f0, fu, &bj->fwd_tiny0[l], &bj->fwd_tinyn[l], &bj->fwd_tinys[l]);
+    for (int i = bj->fwd_tiny0[l]; i < bj->fwd_tiny0[l] + bj->fwd_tinyn[l]; ++i) bj->fwd_tiny_bytes[l] += 8.0 * kl[i] * 32;
     bj->fwd_unit_ptr[l + 1] = (int)fu.size();
     // backward
     lst.clear();
@@ -640,6 +643,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     kl.assign(bp.size(), 0);
     for (size_t i = b0; i < bp.size(); ++i) kl[i] = bp[i].klen;
     make_units(kl, b0, (int)bp.size() - b0, bu, &bj->bwd_tiny0[l], &bj->bwd_tinyn[l], &bj->bwd_tinys[l]);
+    for (int i = bj->bwd_tiny0[l]; i < bj->bwd_tiny0[l] + bj->bwd_tinyn[l]; ++i) bj->bwd_tiny_bytes[l] += 8.0 * kl[i] * 32;
     bj->bwd_unit_ptr[l + 1] = (int)bu.size();
   }
   bj->fwd_doubles = fdoubles;

@@ -543,7 +543,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
     }
     const int nu = bj->fwd_unit_ptr[l + 1] - bj->fwd_unit_ptr[l];
     if (nu > 0) {
-      prof.mark("fwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->fwd_lvl_bytes[l]);
+      prof.mark("fwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->fwd_lvl_bytes[l] - bj->fwd_tiny_bytes[l]);
       a.units = bj->fwd_units + bj->fwd_unit_ptr[l];
       a.panels = bj->fwd_panels;
       a.data = bj->fwd_data;
@@ -551,7 +551,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       PCU_LAUNCH_CHECK(c);
     }
     if (bj->fwd_tinyn[l] > 0) {
-      prof.mark("fwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->fwd_tinyn[l]) + "/" + std::to_string(bj->fwd_tinys[l]), 0.0);
+      prof.mark("fwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->fwd_tinyn[l]) + "/" + std::to_string(bj->fwd_tinys[l]), bj->fwd_tiny_bytes[l]);
       a.panels = bj->fwd_panels;
       a.data = bj->fwd_data;
       launch_tiny<T, true>(bj->fwd_tiny0[l], bj->fwd_tinyn[l], bj->fwd_tinys[l], st, a);
@@ -562,7 +562,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   for (int l = bj->nlevels - 1; l >= 0; --l) {
     const int nu = bj->bwd_unit_ptr[l + 1] - bj->bwd_unit_ptr[l];
     if (nu > 0) {
-      prof.mark("bwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->bwd_lvl_bytes[l]);
+      prof.mark("bwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->bwd_lvl_bytes[l] - bj->bwd_tiny_bytes[l]);
       a.units = bj->bwd_units + bj->bwd_unit_ptr[l];
       a.panels = bj->bwd_panels;
       a.data = bj->bwd_data;
@@ -570,7 +570,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       PCU_LAUNCH_CHECK(c);
     }
     if (bj->bwd_tinyn[l] > 0) {
-      prof.mark("bwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->bwd_tinyn[l]) + "/" + std::to_string(bj->bwd_tinys[l]), 0.0);
+      prof.mark("bwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->bwd_tinyn[l]) + "/" + std::to_string(bj->bwd_tinys[l]), bj->bwd_tiny_bytes[l]);
       a.panels = bj->bwd_panels;
       a.data = bj->bwd_data;
       launch_tiny<T, false>(bj->bwd_tiny0[l], bj->bwd_tinyn[l], bj->bwd_tinys[l], st, a);

@@ -14,6 +14,20 @@ int METIS_NodeND(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, 
                  int64_t* perm, int64_t* iperm);
 }
 
+// METIS draws its random numbers from libc's rand(): one process-wide state behind a lock. Eight concurrent
+// METIS_NodeND calls then run 3x slower than one alone (measured: 11.5 s against 3.6 s for a 64^3 block) and give
+// a different ordering every run. These definitions are hidden, so only the METIS objects linked into this
+// library bind to them: a thread-local 64-bit LCG, re-seeded by METIS at the start of every call -- concurrent
+// calls neither wait for each other nor disturb each other's sequence, and an ordering depends on its graph only.
+extern "C" {
+static thread_local unsigned long long pcu_rand_state = 4321ULL;
+__attribute__((visibility("hidden"))) void srand(unsigned int seed) { pcu_rand_state = seed; }
+__attribute__((visibility("hidden"))) int rand(void) {
+  pcu_rand_state = pcu_rand_state * 6364136223846793005ULL + 1442695040888963407ULL;
+  return (int)((pcu_rand_state >> 33) & 0x7fffffffULL);
+}
+}
+
 namespace pcu {
 namespace {
 
