@@ -228,7 +228,7 @@ static void descent_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
  * ADAPT_BS: small dense algebra on the host (t <= 32, column-major) -- stands in for LAPACKE_dpotrf,
  * cblas_dtrsm, LAPACKE_dgesvd('O','N'), dgeqrf and dormqr on t x t data (ref: ecg.c:431-479).
  * ------------------------------------------------------------------------------------------------ */
-static int h_chol_upper(int n, double* A, int lda) {  /* A = U^T U, upper triangle in place */
+int pa_h_chol_upper(int n, double* A, int lda) {  /* A = U^T U, upper triangle in place */
   for (int j = 0; j < n; ++j) {
     double d = A[j + (size_t)lda * j];
     for (int k = 0; k < j; ++k) d -= A[k + (size_t)lda * j] * A[k + (size_t)lda * j];
@@ -244,7 +244,7 @@ static int h_chol_upper(int n, double* A, int lda) {  /* A = U^T U, upper triang
   return 0;
 }
 
-static void h_triu_inv(int n, const double* U, int ldu, double* Ui, int ldi) {
+void pa_h_triu_inv(int n, const double* U, int ldu, double* Ui, int ldi) {
   for (int j = 0; j < n; ++j) {
     for (int i = 0; i < n; ++i) Ui[i + (size_t)ldi * j] = 0.0;
     Ui[j + (size_t)ldi * j] = 1.0 / U[j + (size_t)ldu * j];
@@ -259,7 +259,7 @@ static void h_triu_inv(int n, const double* U, int ldu, double* Ui, int ldi) {
 /* Left singular vectors and singular values of the t x n matrix A (column-major, lda): one-sided Jacobi on
  * the rows of A.  On return rows[i*n .. i*n+n) = i-th row of Q^T A (row-major), sv descending, Q t x t
  * column-major (ldq = t). */
-static void h_left_svd(int t, int n, const double* A, int lda, double* sv, double* Q, double* rows) {
+void pa_h_left_svd(int t, int n, const double* A, int lda, double* sv, double* Q, double* rows) {
   for (int i = 0; i < t; ++i) for (int c = 0; c < n; ++c) rows[(size_t)i * n + c] = A[i + (size_t)lda * c];
   for (int i = 0; i < t * t; ++i) Q[i] = 0.0;
   for (int i = 0; i < t; ++i) Q[i + (size_t)t * i] = 1.0;
@@ -332,10 +332,10 @@ static void adapt_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   pa_cuda_check(pcu_d2h(c, G, sm_G(p), sizeof(double) * 2 * (size_t)T * T), "pcu_d2h");
   const double* Gpr = G + (size_t)T * T;
   t0 = pa_wtime();
-  h_chol_upper(bs, G, T);  /* Orthodir ignores dpotrf's return code (ref: ecg.c:431) */
+  pa_h_chol_upper(bs, G, T);  /* Orthodir ignores dpotrf's return code (ref: ecg.c:431) */
   ecg->potrf_t += pa_wtime() - t0;
   t0 = pa_wtime();
-  h_triu_inv(bs, G, T, Ui, bs);
+  pa_h_triu_inv(bs, G, T, Ui, bs);
   for (int j = 0; j < T; ++j)      /* alpha = U^-T Gpr[:bs, :] (bs x T, ld bs) */
     for (int i = 0; i < bs; ++i) {
       double v = 0.0;
@@ -344,7 +344,7 @@ static void adapt_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
     }
   ecg->trsm_t += pa_wtime() - t0;
   t0 = pa_wtime();
-  h_left_svd(bs, T, alpha, bs, sv, Q, rows);
+  pa_h_left_svd(bs, T, alpha, bs, sv, Q, rows);
   ecg->gesvd_t += pa_wtime() - t0;
   const double cut = ecg->tol * ecg->normb / sqrt((double)T);  /* ref: ecg.c:420 */
   int t1 = 0;
@@ -449,7 +449,7 @@ int _preAlps_ECGIterateOdir(preAlps_ECG_t* ecg, int* rci_request) {
 /* Cholesky with complete (diagonal) pivoting of the symmetric n x n matrix A (column-major, full storage):
  * A[piv, piv] = U^T U, stops at the first pivot <= tol; tol < 0 selects LAPACK's default n * eps * max(diag)
  * (stands in for LAPACKE_dpstrf('U'), ref: ecg.c:375).  U is returned in the upper triangle of A. */
-static int h_pivoted_chol(int n, double* A, int lda, int* piv, double tol) {
+int pa_h_pivoted_chol(int n, double* A, int lda, int* piv, double tol) {
   double dmax = 0.0;
   for (int i = 0; i < n; ++i) { piv[i] = i; if (A[i + (size_t)lda * i] > dmax) dmax = A[i + (size_t)lda * i]; }
   if (tol < 0.0) tol = n * 1.1102230246251565e-16 * dmax;
@@ -488,13 +488,13 @@ static void omin_rrqr(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   pa_cuda_check(pcu_d2h(c, C, sm_G(p), sizeof(double) * (size_t)T * T), "pcu_d2h");
   for (int j = 0; j < T; ++j) for (int i = j + 1; i < T; ++i) C[i + (size_t)T * j] = C[j + (size_t)T * i];  /* 'U' triangle */
   t0 = pa_wtime();
-  const int rank = h_pivoted_chol(T, C, T, piv, -1.0);
+  const int rank = pa_h_pivoted_chol(T, C, T, piv, -1.0);
   ecg->pstrf_t += pa_wtime() - t0;
   if (rank < T)
     CPLM_Abort("ADAPT_BS with ORTHOMIN: the new search directions lost rank (%d of %d); the reduction itself is not "
                "implemented (the reference's own handling of this case is inconsistent, ecg.c:357-366)", rank, T);
   t0 = pa_wtime();
-  h_triu_inv(T, C, T, Ui, T);
+  pa_h_triu_inv(T, C, T, Ui, T);
   for (int i = 0; i < T * T; ++i) Wneg[i] = 0.0;
   for (int j = 0; j < T; ++j) for (int k = 0; k <= j; ++k) Wneg[piv[k] + (size_t)T * j] = -Ui[k + (size_t)T * j];
   pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
@@ -558,9 +558,9 @@ static int fused_adapt_step(preAlps_ECG_t* ecg, ecg_priv_t* p, const double* H) 
   double mu[32 * 32], Ui[32 * 32], alpha[32 * 32], Q[32 * 32], rows[32 * 32], sv[32];
   for (int i = 0; i < T * T; ++i) mu[i] = H[3 * (size_t)T * T + i];
   double t0 = pa_wtime();
-  h_chol_upper(bs, mu, T);
+  pa_h_chol_upper(bs, mu, T);
   ecg->potrf_t += pa_wtime() - t0;
-  h_triu_inv(bs, mu, T, Ui, bs);
+  pa_h_triu_inv(bs, mu, T, Ui, bs);
   for (int j = 0; j < T; ++j)
     for (int i = 0; i < bs; ++i) {
       double v = 0.0;
@@ -568,7 +568,7 @@ static int fused_adapt_step(preAlps_ECG_t* ecg, ecg_priv_t* p, const double* H) 
       alpha[i + (size_t)bs * j] = v;
     }
   t0 = pa_wtime();
-  h_left_svd(bs, T, alpha, bs, sv, Q, rows);
+  pa_h_left_svd(bs, T, alpha, bs, sv, Q, rows);
   ecg->gesvd_t += pa_wtime() - t0;
   const double cut = ecg->tol * ecg->normb / sqrt((double)T);
   int t1 = 0;

@@ -73,4 +73,10 @@ int pa_is_device_block(const CPLM_Mat_Dense_t* X);
 void pa_allreduce_dev(double* dbuf, int n, double* comm_t);
 double pa_wtime(void);
 
+/* small dense algebra of the ADAPT_BS paths (pa_ecg.c), column-major, n <= 32; exported for the CPU tests */
+int pa_h_chol_upper(int n, double* A, int lda);
+void pa_h_triu_inv(int n, const double* U, int ldu, double* Ui, int ldi);
+void pa_h_left_svd(int t, int n, const double* A, int lda, double* sv, double* Q, double* rows);
+int pa_h_pivoted_chol(int n, double* A, int lda, int* piv, double tol);
+
 #endif
