@@ -93,10 +93,21 @@ struct SweepArgs {
   double* scratch; int* counters;   // inter-CTA split-K
 };
 
-__device__ __forceinline__ double2 ld_stream2(const double* p) {
-  double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
+// one 256-bit load per lane (SASS LDG.E.NA.EFL2.256): the 32 bytes a lane owns of a k-block, not allocated in L1 and
+// first in line for eviction from L2 -- the panels are streamed once per apply (19 GB) and must not push the block
+// vectors (update rows, ancestor rows gathered by the backward sweep) out of the 126 MB L2
+__device__ __forceinline__ void ld_stream4(const double* p, double2& a, double2& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+               : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_stream(void* smem_dst, const void* gmem_src, unsigned long long pol) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
   auto issue = [&](int kb, double2& m0, double2& m1) {
     if (kb < q1) {
       const double* p = base + (size_t)kb * 128;
-      if (NOALLOC) { m0 = ld_stream2(p); m1 = ld_stream2(p + 2); }
+      if (NOALLOC) ld_stream4(p, m0, m1);
       else { m0 = __ldg(reinterpret_cast<const double2*>(p)); m1 = __ldg(reinterpret_cast<const double2*>(p + 2)); }
     } else {
       m0 = make_double2(0.0, 0.0);
@@ -360,9 +371,10 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
   const int nkb = klen >> 2;
   const double* base = a.data + off + lane * 4;
   const int* rows = a.rows + rows_off;
+  const unsigned long long pol = l2_evict_first_policy();
   for (int kb = 0; kb < nkb; ++kb) {
-    cp_async16(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128);
-    cp_async16(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2);
+    cp_async16_stream(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128, pol);
+    cp_async16_stream(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2, pol);
   }
   pdl_wait();   // the panel itself is static; the input rows come from the previous kernel
   pdl_launch_dependents();
