@@ -28,7 +28,7 @@ struct SpmmArgs {
   const int* rowPtr;
   const int* colInd;
   const double* val;
-  const int* blk;  // row-block boundaries, nblk+1
+  const int4* blk;  // per row block: {first row, end row, first entry, end entry} -- one load instead of a chain of three
   int m;
   const double* X;
   int ldx;
@@ -42,18 +42,26 @@ __device__ __forceinline__ double2 ldg2(const double* p) {
   return __ldg(reinterpret_cast<const double2*>(p));
 }
 
-// T columns, G lanes per row, each lane owns columns {2*lig, 2*lig+1} (T >= 2) or column 0 (T == 1).
-template <int T>
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): 4 columns of a row per lane
+__device__ __forceinline__ void ldg4(const double* p, double (&x)[4]) {
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg4(double* p, const double (&x)[4]) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+}
+
+// T columns, G = T / CPL lanes per row, each lane owns CPL adjacent columns: 4 with 256-bit accesses (T >= 8, rows
+// 32-byte aligned: half the lanes, so twice the rows per warp and half the instructions per row), else 2, or 1 (T == 1).
+template <int T, int CPL>
 __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
-  constexpr int CPL = (T >= 2) ? 2 : 1;
   constexpr int G = T / CPL;
   constexpr int NG = kThreads / G;
   __shared__ int s_col[kNnzCap];
   __shared__ double s_val[kNnzCap];
   __shared__ int s_rp[kRowCap + 1];
 
-  const int r0 = a.blk[blockIdx.x], r1 = a.blk[blockIdx.x + 1];
-  const int p0 = a.rowPtr[r0], p1 = a.rowPtr[r1];
+  const int4 d = __ldg(a.blk + blockIdx.x);
+  const int r0 = d.x, r1 = d.y, p0 = d.z, p1 = d.w;
   const int n = p1 - p0;
   const int tid = threadIdx.x;
 
@@ -67,6 +75,21 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
     const int grp = tid / G, lig = tid % G;
     for (int r = r0 + grp; r < r1; r += NG) {
       const int b = s_rp[r - r0], e = s_rp[r - r0 + 1];
+      if (CPL == 4) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+        for (int p = b; p < e; ++p) {
+          const int c = s_col[p];
+          const double v = s_val[p];
+          const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * a.t;
+          double x[4];
+          ldg4(src + 4 * lig, x);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fma(v, x[j], acc[j]);
+        }
+        stg4(a.Y + (size_t)r * a.ldy + 4 * lig, acc);
+        continue;
+      }
       double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll 4
       for (int p = b; p < e; ++p) {
@@ -120,7 +143,8 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel_generic(SpmmArgs a) {
   constexpr int G = 16, NG = kThreads / G;
   __shared__ int s_col[kNnzCap];
   __shared__ double s_val[kNnzCap];
-  const int r0 = a.blk[blockIdx.x], r1 = a.blk[blockIdx.x + 1];
+  const int4 d = __ldg(a.blk + blockIdx.x);
+  const int r0 = d.x, r1 = d.y;
   const int tid = threadIdx.x, grp = tid / G, lig = tid % G;
   const int t = a.t;
   // rows are processed in sub-blocks that fit the staging buffers
@@ -184,7 +208,7 @@ struct pcu_spmm {
   int* d_rowPtr = nullptr;
   int* d_colInd = nullptr;
   double* d_val = nullptr;
-  int* d_blk = nullptr;
+  int4* d_blk = nullptr;
   int nblk = 0;
   bool vec_ok = true;  // all row blocks fit the staging buffers or are single rows
   // halo
@@ -228,24 +252,23 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
     PCU_CHECK(colInd[p] >= 0 && colInd[p] < m + nhalo, "pcu_spmm_create: column index %d out of range at %lld",
               colInd[p], (long long)p);
   // row blocks: <= kRowCap rows and <= kNnzCap entries; an over-long row gets a block of its own
-  std::vector<int> blk;
-  blk.push_back(0);
+  std::vector<int4> blk;
   for (int r = 0; r < m;) {
     int e = r;
     while (e < m && e - r < kRowCap && rowPtr[e + 1] - rowPtr[r] <= kNnzCap) ++e;
     if (e == r) e = r + 1;
-    blk.push_back(e);
+    blk.push_back(make_int4(r, e, rowPtr[r], rowPtr[e]));
     r = e;
   }
-  op->nblk = (int)blk.size() - 1;
+  op->nblk = (int)blk.size();
   PCU_CUDA(cudaMalloc(&op->d_rowPtr, sizeof(int) * (size_t)(m + 1)));
   PCU_CUDA(cudaMalloc(&op->d_colInd, sizeof(int) * (size_t)std::max<int64_t>(op->nnz, 1)));
   PCU_CUDA(cudaMalloc(&op->d_val, sizeof(double) * (size_t)std::max<int64_t>(op->nnz, 1)));
-  PCU_CUDA(cudaMalloc(&op->d_blk, sizeof(int) * blk.size()));
+  PCU_CUDA(cudaMalloc(&op->d_blk, sizeof(int4) * std::max<size_t>(blk.size(), 1)));
   PCU_CUDA(cudaMemcpy(op->d_rowPtr, rowPtr, sizeof(int) * (size_t)(m + 1), cudaMemcpyHostToDevice));
   PCU_CUDA(cudaMemcpy(op->d_colInd, colInd, sizeof(int) * (size_t)op->nnz, cudaMemcpyHostToDevice));
   PCU_CUDA(cudaMemcpy(op->d_val, val, sizeof(double) * (size_t)op->nnz, cudaMemcpyHostToDevice));
-  PCU_CUDA(cudaMemcpy(op->d_blk, blk.data(), sizeof(int) * blk.size(), cudaMemcpyHostToDevice));
+  if (!blk.empty()) PCU_CUDA(cudaMemcpy(op->d_blk, blk.data(), sizeof(int4) * blk.size(), cudaMemcpyHostToDevice));
   *out = op;
   return 0;
 }
@@ -324,14 +347,28 @@ int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, i
   SpmmArgs a{op->d_rowPtr, op->d_colInd, op->d_val, op->d_blk, op->m, X, ldx, op->d_halo, Y, ldy, t};
   const bool aligned = (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0);
   const bool pow2 = (t == 2 || t == 4 || t == 8 || t == 16 || t == 32);
-  if (t == 1) spmm_kernel<1><<<op->nblk, kThreads, 0, c->stream>>>(a);
+  // 256-bit accesses need 32-byte aligned rows (the halo buffer has ld = t). They pay for short rows, where the
+  // per-row instructions dominate and twice the rows per warp halves them (7-point: 126 -> 112 us at t = 8); with 27
+  // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
+  const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
+                    ((uintptr_t)op->d_halo % 32 == 0) && op->nnz <= 12 * (int64_t)op->m;
+  if (t == 1) spmm_kernel<1, 1><<<op->nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {
-      case 2: spmm_kernel<2><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
-      case 4: spmm_kernel<4><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
-      case 8: spmm_kernel<8><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
-      case 16: spmm_kernel<16><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
-      default: spmm_kernel<32><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      case 2: spmm_kernel<2, 2><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      case 4: spmm_kernel<4, 2><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      case 8:
+        if (wide) spmm_kernel<8, 4><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        else spmm_kernel<8, 2><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        break;
+      case 16:
+        if (wide) spmm_kernel<16, 4><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        else spmm_kernel<16, 2><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        break;
+      default:
+        if (wide) spmm_kernel<32, 4><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        else spmm_kernel<32, 2><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        break;
     }
   } else {
     spmm_kernel_generic<<<op->nblk, kThreads, 0, c->stream>>>(a);
