@@ -21,8 +21,13 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kNnzCap = 1536;   // staged entries per CTA: 18 KB of shared memory (5 CTAs/SM; 3072/256 rows was 15 % slower)
-constexpr int kRowCap = 128;
+constexpr int kNnzCap = 1792;   // staged entries per CTA (21 KB of shared memory) and rows per CTA: the static arrays
+constexpr int kRowCap = 256;    // are sized for the larger of the two row-block shapes below
+// Row blocks come in two shapes. With few lanes per row (t <= 4) a CTA covers many rows per pass and larger blocks
+// amortise the descriptor + staging latency (7-point, t = 1: 78 -> 61 us); from t = 8 up the smaller blocks win
+// (t = 32: 289 vs 316 us): more CTAs in different phases per SM.
+constexpr int kShapeRows[2] = {128, 256};
+constexpr int kShapeNnz[2] = {1536, 1792};
 
 struct SpmmArgs {
   const int* rowPtr;
@@ -208,8 +213,8 @@ struct pcu_spmm {
   int* d_rowPtr = nullptr;
   int* d_colInd = nullptr;
   double* d_val = nullptr;
-  int4* d_blk = nullptr;
-  int nblk = 0;
+  int4* d_blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
+  int nblk[2] = {0, 0};
   bool vec_ok = true;  // all row blocks fit the staging buffers or are single rows
   // halo
   int nnbr = 0;
@@ -252,23 +257,27 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
     PCU_CHECK(colInd[p] >= 0 && colInd[p] < m + nhalo, "pcu_spmm_create: column index %d out of range at %lld",
               colInd[p], (long long)p);
   // row blocks: <= kRowCap rows and <= kNnzCap entries; an over-long row gets a block of its own
-  std::vector<int4> blk;
-  for (int r = 0; r < m;) {
-    int e = r;
-    while (e < m && e - r < kRowCap && rowPtr[e + 1] - rowPtr[r] <= kNnzCap) ++e;
-    if (e == r) e = r + 1;
-    blk.push_back(make_int4(r, e, rowPtr[r], rowPtr[e]));
-    r = e;
+  std::vector<int4> blk[2];
+  for (int sh = 0; sh < 2; ++sh) {
+    for (int r = 0; r < m;) {
+      int e = r;
+      while (e < m && e - r < kShapeRows[sh] && rowPtr[e + 1] - rowPtr[r] <= kShapeNnz[sh]) ++e;
+      if (e == r) e = r + 1;
+      blk[sh].push_back(make_int4(r, e, rowPtr[r], rowPtr[e]));
+      r = e;
+    }
+    op->nblk[sh] = (int)blk[sh].size();
   }
-  op->nblk = (int)blk.size();
   PCU_CUDA(cudaMalloc(&op->d_rowPtr, sizeof(int) * (size_t)(m + 1)));
   PCU_CUDA(cudaMalloc(&op->d_colInd, sizeof(int) * (size_t)std::max<int64_t>(op->nnz, 1)));
   PCU_CUDA(cudaMalloc(&op->d_val, sizeof(double) * (size_t)std::max<int64_t>(op->nnz, 1)));
-  PCU_CUDA(cudaMalloc(&op->d_blk, sizeof(int4) * std::max<size_t>(blk.size(), 1)));
+  for (int sh = 0; sh < 2; ++sh) PCU_CUDA(cudaMalloc(&op->d_blk[sh], sizeof(int4) * std::max<size_t>(blk[sh].size(), 1)));
   PCU_CUDA(cudaMemcpy(op->d_rowPtr, rowPtr, sizeof(int) * (size_t)(m + 1), cudaMemcpyHostToDevice));
   PCU_CUDA(cudaMemcpy(op->d_colInd, colInd, sizeof(int) * (size_t)op->nnz, cudaMemcpyHostToDevice));
   PCU_CUDA(cudaMemcpy(op->d_val, val, sizeof(double) * (size_t)op->nnz, cudaMemcpyHostToDevice));
-  if (!blk.empty()) PCU_CUDA(cudaMemcpy(op->d_blk, blk.data(), sizeof(int4) * blk.size(), cudaMemcpyHostToDevice));
+  for (int sh = 0; sh < 2; ++sh)
+    if (!blk[sh].empty())
+      PCU_CUDA(cudaMemcpy(op->d_blk[sh], blk[sh].data(), sizeof(int4) * blk[sh].size(), cudaMemcpyHostToDevice));
   *out = op;
   return 0;
 }
@@ -277,7 +286,7 @@ int pcu_spmm_destroy(pcu_spmm* op) {
   if (!op) return 0;
   cudaSetDevice(op->ctx->device);
   cudaStreamSynchronize(op->ctx->stream);
-  cudaFree(op->d_rowPtr); cudaFree(op->d_colInd); cudaFree(op->d_val); cudaFree(op->d_blk);
+  cudaFree(op->d_rowPtr); cudaFree(op->d_colInd); cudaFree(op->d_val); cudaFree(op->d_blk[0]); cudaFree(op->d_blk[1]);
   if (op->d_send_idx) cudaFree(op->d_send_idx);
   if (op->d_sendbuf) cudaFree(op->d_sendbuf);
   if (op->d_halo) cudaFree(op->d_halo);
@@ -344,7 +353,9 @@ int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, i
   if (op->m == 0) return 0;
   if (op->nhalo > 0 && ensure_halo_buffers(op, t)) return 1;
   PCU_CHECK(t <= 32, "pcu_spmm_apply: t=%d > 32 is not supported", t);
-  SpmmArgs a{op->d_rowPtr, op->d_colInd, op->d_val, op->d_blk, op->m, X, ldx, op->d_halo, Y, ldy, t};
+  const int sh = (t <= 4) ? 1 : 0;
+  const int nblk = op->nblk[sh];
+  SpmmArgs a{op->d_rowPtr, op->d_colInd, op->d_val, op->d_blk[sh], op->m, X, ldx, op->d_halo, Y, ldy, t};
   const bool aligned = (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0);
   const bool pow2 = (t == 2 || t == 4 || t == 8 || t == 16 || t == 32);
   // 256-bit accesses need 32-byte aligned rows (the halo buffer has ld = t). They pay for short rows, where the
@@ -352,26 +363,26 @@ int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, i
   // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
   const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
                     ((uintptr_t)op->d_halo % 32 == 0) && op->nnz <= 12 * (int64_t)op->m;
-  if (t == 1) spmm_kernel<1, 1><<<op->nblk, kThreads, 0, c->stream>>>(a);
+  if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {
-      case 2: spmm_kernel<2, 2><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
-      case 4: spmm_kernel<4, 2><<<op->nblk, kThreads, 0, c->stream>>>(a); break;
+      case 2: spmm_kernel<2, 2><<<nblk, kThreads, 0, c->stream>>>(a); break;
+      case 4: spmm_kernel<4, 2><<<nblk, kThreads, 0, c->stream>>>(a); break;
       case 8:
-        if (wide) spmm_kernel<8, 4><<<op->nblk, kThreads, 0, c->stream>>>(a);
-        else spmm_kernel<8, 2><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        if (wide) spmm_kernel<8, 4><<<nblk, kThreads, 0, c->stream>>>(a);
+        else spmm_kernel<8, 2><<<nblk, kThreads, 0, c->stream>>>(a);
         break;
       case 16:
-        if (wide) spmm_kernel<16, 4><<<op->nblk, kThreads, 0, c->stream>>>(a);
-        else spmm_kernel<16, 2><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        if (wide) spmm_kernel<16, 4><<<nblk, kThreads, 0, c->stream>>>(a);
+        else spmm_kernel<16, 2><<<nblk, kThreads, 0, c->stream>>>(a);
         break;
       default:
-        if (wide) spmm_kernel<32, 4><<<op->nblk, kThreads, 0, c->stream>>>(a);
-        else spmm_kernel<32, 2><<<op->nblk, kThreads, 0, c->stream>>>(a);
+        if (wide) spmm_kernel<32, 4><<<nblk, kThreads, 0, c->stream>>>(a);
+        else spmm_kernel<32, 2><<<nblk, kThreads, 0, c->stream>>>(a);
         break;
     }
   } else {
-    spmm_kernel_generic<<<op->nblk, kThreads, 0, c->stream>>>(a);
+    spmm_kernel_generic<<<nblk, kThreads, 0, c->stream>>>(a);
   }
   PCU_LAUNCH_CHECK(c);
   return 0;
