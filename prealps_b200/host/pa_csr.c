@@ -415,7 +415,103 @@ int pa_halo_map(const CPLM_Mat_CSR_t* A, int g0, int g1, int** halo_out, int* nh
 
 /* synthetic operators of SURVEY.md 8(d): N^3 grid, lexicographic (x fastest), Dirichlet by truncation.
  * kind 0: a_ii = 6, -1 for the 6 face neighbours; kind 1: a_ii = 26, -1 for the 26 neighbours. */
+/* kind 2: trilinear (Q1) hexahedral elements for 3D linear elasticity on N^3 nodes, 3 dof per node (up to 81
+ * non-zeros per row), the face x = 0 clamped (those dof eliminated), Young's modulus 1 or 1e3 in layers of two
+ * elements along z, nu = 0.3 -- the operator of BASELINE config 4, same definition as
+ * oracle/gen_matrices.py: elasticity3d (tests/test_host_integer.py compares the two). */
+static void hex_stiffness(double nu, double K[24][24]) {
+  const double lam = nu / ((1 + nu) * (1 - 2 * nu)), mu = 1.0 / (2 * (1 + nu));
+  double D[6][6] = {{0}};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) D[i][j] = lam;
+  for (int i = 0; i < 3; ++i) D[i][i] += 2 * mu;
+  for (int i = 3; i < 6; ++i) D[i][i] = mu;
+  const double g[2] = {0.5 - 1.0 / (2 * sqrt(3.0)), 0.5 + 1.0 / (2 * sqrt(3.0))};
+  for (int i = 0; i < 24; ++i) for (int j = 0; j < 24; ++j) K[i][j] = 0.0;
+  for (int gz = 0; gz < 2; ++gz) for (int gy = 0; gy < 2; ++gy) for (int gx = 0; gx < 2; ++gx) {
+    const double pt[3] = {g[gx], g[gy], g[gz]};
+    double B[6][24] = {{0}};
+    for (int a = 0; a < 8; ++a) {  /* corner a = (x fastest): (a&1, (a>>1)&1, a>>2) */
+      const int cx[3] = {a & 1, (a >> 1) & 1, a >> 2};
+      double f[3], sg[3];
+      for (int d = 0; d < 3; ++d) { f[d] = cx[d] ? pt[d] : 1 - pt[d]; sg[d] = cx[d] ? 1.0 : -1.0; }
+      const double dx = sg[0] * f[1] * f[2], dy = f[0] * sg[1] * f[2], dz = f[0] * f[1] * sg[2];
+      B[0][3 * a] = dx; B[1][3 * a + 1] = dy; B[2][3 * a + 2] = dz;
+      B[3][3 * a] = dy; B[3][3 * a + 1] = dx;
+      B[4][3 * a + 1] = dz; B[4][3 * a + 2] = dy;
+      B[5][3 * a] = dz; B[5][3 * a + 2] = dx;
+    }
+    for (int i = 0; i < 24; ++i)
+      for (int j = 0; j < 24; ++j) {
+        double v = 0.0;
+        for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q) v += B[p][i] * D[p][q] * B[q][j];
+        K[i][j] += v / 8.0;
+      }
+  }
+  for (int i = 0; i < 24; ++i) for (int j = i + 1; j < 24; ++j) { const double v = 0.5 * (K[i][j] + K[j][i]); K[i][j] = K[j][i] = v; }
+}
+
+static int elasticity_csr(int N, CPLM_Mat_CSR_t* A) {
+  const long long nfree_nodes = (long long)(N - 1) * N * N;
+  const long long M = 3 * nfree_nodes;
+  if (N < 2) CPLM_Abort("elasticity operator needs at least 2 nodes per side");
+  if (M * 81 > 2147483647LL) CPLM_Abort("elasticity operator too large for 32-bit indices");
+  double K[24][24];
+  hex_stiffness(0.3, K);
+  /* free node id of node (x >= 1, y, z): nodes are numbered x fastest and every (y, z) line loses its x = 0 node */
+#define FREE_ID(x, y, z) ((((long long)(z) * N + (y)) * (N - 1)) + ((x) - 1))
+  double kmax = 0.0;
+  for (int i = 0; i < 24; ++i) for (int j = 0; j < 24; ++j) if (fabs(K[i][j]) > kmax) kmax = fabs(K[i][j]);
+  const double tiny = 1e-12 * kmax;  /* couplings that vanish analytically come out as rounding noise: not stored */
+  A->rowPtr = (int*)pa_xmalloc(sizeof(int) * ((size_t)M + 1));
+  A->colInd = NULL; A->val = NULL;
+  long long nnz = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      A->colInd = (int*)pa_xmalloc(sizeof(int) * (size_t)nnz);
+      A->val = (double*)pa_xmalloc(sizeof(double) * (size_t)nnz);
+    }
+    long long pos = 0;
+    for (int z = 0; z < N; ++z) for (int y = 0; y < N; ++y) for (int x = 1; x < N; ++x) {
+      const long long r = 3 * FREE_ID(x, y, z);
+      for (int ci = 0; ci < 3; ++ci) {
+        if (pass == 0) A->rowPtr[r + ci] = (int)pos;
+        for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx, yy = y + dy, zz = z + dz;
+          if (xx < 1 || xx >= N || yy < 0 || yy >= N || zz < 0 || zz >= N) continue;
+          double row[3] = {0.0, 0.0, 0.0};
+          double emax = 0.0;
+          /* elements (ex, ey, ez) that contain both nodes, ascending element index */
+          for (int ez = z - 1; ez <= z; ++ez) for (int ey = y - 1; ey <= y; ++ey) for (int ex = x - 1; ex <= x; ++ex) {
+            if (ex < 0 || ex >= N - 1 || ey < 0 || ey >= N - 1 || ez < 0 || ez >= N - 1) continue;
+            if (xx < ex || xx > ex + 1 || yy < ey || yy > ey + 1 || zz < ez || zz > ez + 1) continue;
+            const double E = ((ez / 2) % 2 == 0) ? 1.0 : 1e3;
+            if (E > emax) emax = E;
+            const int a = (x - ex) + 2 * (y - ey) + 4 * (z - ez), b = (xx - ex) + 2 * (yy - ey) + 4 * (zz - ez);
+            for (int cj = 0; cj < 3; ++cj) row[cj] += E * K[3 * a + ci][3 * b + cj];
+          }
+          const long long cfree = 3 * FREE_ID(xx, yy, zz);
+          for (int cj = 0; cj < 3; ++cj) {
+            if (!(fabs(row[cj]) > tiny * emax)) continue;
+            if (pass == 1) { A->colInd[pos] = (int)(cfree + cj); A->val[pos] = row[cj]; }
+            ++pos;
+          }
+        }
+      }
+    }
+    if (pass == 0) { nnz = pos; A->rowPtr[M] = (int)nnz; }
+  }
+#undef FREE_ID
+  memset(&A->info, 0, sizeof A->info);
+  A->info.M = A->info.m = A->info.N = A->info.n = (int)M;
+  A->info.nnz = A->info.lnnz = (int)nnz;
+  A->info.blockSize = 1;
+  A->info.format = FORMAT_CSR;
+  A->info.structure = SYMMETRIC;
+  return 0;
+}
+
 int pa_stencil_csr(int kind, int N, CPLM_Mat_CSR_t* A) {
+  if (kind == 2) return elasticity_csr(N, A);
   const long long M = (long long)N * N * N;
   if (M > 2000000000LL) CPLM_Abort("stencil too large for 32-bit indices");
   const int reach = 1;

@@ -89,6 +89,24 @@ def test_stencil_generators_match_python():
         assert np.array_equal(rp, A.indptr) and np.array_equal(ci, A.indices) and np.array_equal(v, A.data)
 
 
+def test_elasticity_generator_matches_python():
+    """kind 2 = Q1 linear elasticity (BASELINE config 4): same values to rounding, exactly symmetric"""
+    import scipy.sparse as sp
+    for N in (3, 6):
+        A = gen_matrices.elasticity3d(N, N, N)
+        G = capi.MatCSR()
+        assert lib.pa_stencil_csr(2, N, C.byref(G)) == 0
+        rp, ci, v = G.arrays()
+        B = sp.csr_matrix((v, ci, rp), shape=A.shape)
+        assert abs(A - B).max() <= 1e-12 * abs(A).max()
+        assert abs(B - B.T).max() == 0.0
+        # couplings that vanish analytically are not stored (the python generator keeps them as rounding noise)
+        tol = 1e-9 * abs(A).max()
+        Ab = A.copy(); Ab.data[np.abs(Ab.data) < tol] = 0.0; Ab.eliminate_zeros(); Ab.sort_indices()
+        assert np.array_equal(rp, Ab.indptr) and np.array_equal(ci, Ab.indices)
+        assert np.abs(v).min() > tol
+
+
 def test_loader_general_and_zero_based(tmp_path):
     A = gen_matrices.poisson7(4)
     p = tmp_path / "g.mtx"
