@@ -215,7 +215,6 @@ struct pcu_spmm {
   double* d_val = nullptr;
   int4* d_blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
   int nblk[2] = {0, 0};
-  bool vec_ok = true;  // all row blocks fit the staging buffers or are single rows
   // halo
   int nnbr = 0;
   std::vector<int> nbr_rank, send_ptr, recv_ptr;
