@@ -143,6 +143,75 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
   }
 }
 
+// Candidate kernel, opt-in with PREALPS_SPMM_LEAN=1 (written after the last GPU session of round 1: compiled and its
+// SASS read, NOT yet run on a B200 -- measure before making it the default).  Same mapping, same summation order
+// and therefore the same bits as spmm_kernel<T, CPL>; what changes is the work per entry in the row phase.  The
+// SASS of spmm_kernel<8, 4> spends ~22 instructions per entry and lane: LDS col, LDS val, a compare, 4-5 predicated
+// LDC of the kernel arguments, two predicated IMAD.WIDE, four predicated LEA, a 64-bit add, LDG.256 and 4 DFMA.
+// Here the thread that stages an entry (once per entry, 32 entries per warp instruction) resolves "block row or
+// halo row" and the row stride into ONE 64-bit byte offset relative to X, stored next to the value, so the row phase
+// is LDS.128 + 64-bit add + LDG + CPL DFMA per entry.  Needs ldx == T (rows of X and of the halo buffer are both
+// T doubles apart) and every row block of shape 0 within the staging capacity.
+template <int T, int CPL>
+__global__ void __launch_bounds__(kThreads) spmm_lean_kernel(SpmmArgs a) {
+  static_assert(CPL == 2 || CPL == 4, "lanes own 2 or 4 adjacent columns");
+  constexpr int G = T / CPL;
+  constexpr int NG = kThreads / G;
+  constexpr int kCap = kShapeNnz[0];
+  __shared__ double2 s_ent[kCap];  // {value, bit pattern of the source row's byte offset from X}
+  __shared__ int s_rp[kShapeRows[0] + 1];
+
+  const int4 d = __ldg(a.blk + blockIdx.x);
+  const int r0 = d.x, r1 = d.y, p0 = d.z, p1 = d.w;
+  const int n = p1 - p0;  // <= kCap: checked on the host before this kernel is chosen
+  const int tid = threadIdx.x;
+  // halo row c - m lives at H + (c - m) * T doubles = X + hdelta + c * T * 8 bytes (unused without a halo: c < m)
+  const long long hdelta = (long long)(reinterpret_cast<intptr_t>(a.H) - reinterpret_cast<intptr_t>(a.X)) -
+                           (long long)a.m * (T * 8);
+  for (int i = tid; i < n; i += kThreads) {
+    const int c = __ldg(a.colInd + p0 + i);
+    const long long off = (long long)c * (T * 8) + (c < a.m ? 0ll : hdelta);
+    s_ent[i] = make_double2(__ldg(a.val + p0 + i), __longlong_as_double(off));
+  }
+  for (int i = tid; i <= r1 - r0; i += kThreads) s_rp[i] = __ldg(a.rowPtr + r0 + i) - p0;
+  __syncthreads();
+  const int grp = tid / G, lig = tid % G;
+  const char* xl = reinterpret_cast<const char*>(a.X + CPL * lig);
+  for (int r = r0 + grp; r < r1; r += NG) {
+    const int b = s_rp[r - r0], e = s_rp[r - r0 + 1];
+    double acc[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[j] = 0.0;
+#pragma unroll 4
+    for (int p = b; p < e; ++p) {
+      const double2 en = s_ent[p];
+      const double* src = reinterpret_cast<const double*>(xl + __double_as_longlong(en.y));
+      if constexpr (CPL == 4) {
+        double x[4];
+        ldg4(src, x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fma(en.x, x[j], acc[j]);
+      } else {
+        const double2 x = ldg2(src);
+        acc[0] = fma(en.x, x.x, acc[0]);
+        acc[1] = fma(en.x, x.y, acc[1]);
+      }
+    }
+    double* dst = a.Y + (size_t)r * a.ldy + CPL * lig;
+    if constexpr (CPL == 4) {
+      stg4(dst, acc);
+    } else {
+      *reinterpret_cast<double2*>(dst) = make_double2(acc[0], acc[1]);
+    }
+  }
+}
+
+template <int T>
+void launch_lean(const SpmmArgs& a, int nblk, bool wide, cudaStream_t st) {
+  if (wide) spmm_lean_kernel<T, 4><<<nblk, kThreads, 0, st>>>(a);
+  else spmm_lean_kernel<T, 2><<<nblk, kThreads, 0, st>>>(a);
+}
+
 // any 1 <= t <= 32: 16 lanes per row, lane owns columns lig and lig+16
 __global__ void __launch_bounds__(kThreads) spmm_kernel_generic(SpmmArgs a) {
   constexpr int G = 16, NG = kThreads / G;
@@ -215,6 +284,7 @@ struct pcu_spmm {
   double* d_val = nullptr;
   int4* d_blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
   int nblk[2] = {0, 0};
+  bool lean = false;  // PREALPS_SPMM_LEAN=1 and every shape-0 row block fits the staging buffer: spmm_lean_kernel from t = 8 up
   // halo
   int nnbr = 0;
   std::vector<int> nbr_rank, send_ptr, recv_ptr;
@@ -266,6 +336,11 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
       r = e;
     }
     op->nblk[sh] = (int)blk[sh].size();
+  }
+  if (const char* e = getenv("PREALPS_SPMM_LEAN")) {
+    op->lean = atoi(e) != 0;
+    for (const int4& b : blk[0])
+      if (b.w - b.z > kShapeNnz[0]) op->lean = false;
   }
   PCU_CUDA(cudaMalloc(&op->d_rowPtr, sizeof(int) * (size_t)(m + 1)));
   PCU_CUDA(cudaMalloc(&op->d_colInd, sizeof(int) * (size_t)std::max<int64_t>(op->nnz, 1)));
@@ -362,7 +437,12 @@ int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, i
   // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
   const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
                     ((uintptr_t)op->d_halo % 32 == 0) && op->nnz <= 12 * (int64_t)op->m;
-  if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
+  const bool lean = op->lean && aligned && pow2 && t >= 8 && ldx == t;
+  if (lean) {
+    if (t == 8) launch_lean<8>(a, nblk, wide, c->stream);
+    else if (t == 16) launch_lean<16>(a, nblk, wide, c->stream);
+    else launch_lean<32>(a, nblk, wide, c->stream);
+  } else if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {
       case 2: spmm_kernel<2, 2><<<nblk, kThreads, 0, c->stream>>>(a); break;

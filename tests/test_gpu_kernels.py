@@ -1,5 +1,6 @@
 """Kernel-level parity on the GPU through the C ABI of libprealps_cuda (include/prealps_cuda.h)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -54,6 +55,46 @@ def test_spmm_matches_scipy(dev, t):
     assert np.array_equal(packed, X[[1, 3, 5, 7, 9], :t])
     dev.free(dX, dY)
     cu.pcu_spmm_destroy(op)
+
+
+candidates = pytest.mark.skipif(not os.environ.get("PREALPS_TEST_CANDIDATES"),
+                                reason="opt-in kernels that have not been measured on a B200 yet (PREALPS_TEST_CANDIDATES=1)")
+
+
+@candidates
+@pytest.mark.parametrize("gen,N", [("poisson7", 14), ("stencil27", 9)])
+def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
+    """PREALPS_SPMM_LEAN=1 (spmm_lean_kernel) keeps the mapping and the summation order: same bits as the default kernel"""
+    A = getattr(gen_matrices, gen)(N).tocsr()
+    m = A.shape[0]
+    nh = 53
+    B = sp.random(m, nh, density=0.03, random_state=5, format="csr")
+    Aext = sp.hstack([A, B]).tocsr()
+    Aext.sort_indices()
+    rng = np.random.default_rng(1)
+    out = {}
+    for lean in ("0", "1"):
+        monkeypatch.setenv("PREALPS_SPMM_LEAN", lean)
+        op = C.c_void_p()
+        assert cu.pcu_spmm_create(dev.ctx, m, nh, capi.ip(Aext.indptr.astype(np.int32)), capi.ip(Aext.indices.astype(np.int32)),
+                                  capi.dp(Aext.data), C.byref(op)) == 0, cu.pcu_last_error()
+        assert cu.pcu_spmm_set_halo(op, 1, capi.ip(np.array([0], np.int32)), capi.ip(np.array([0, 0], np.int32)),
+                                    capi.ip(np.zeros(1, np.int32)), capi.ip(np.array([0, nh], np.int32))) == 0
+        cu.pcu_spmm_halo_buffer.restype = C.c_void_p
+        for t in (8, 16, 32):
+            r2 = np.random.default_rng(t)
+            X, H = r2.standard_normal((m, t)), r2.standard_normal((nh, t))
+            hb = cu.pcu_spmm_halo_buffer(op, t)
+            assert cu.pcu_h2d(dev.ctx, C.c_void_p(hb), H.ctypes.data_as(C.c_void_p), C.c_size_t(H.nbytes)) == 0
+            dX, dY = dev.up(X), dev.zeros(m * t)
+            assert cu.pcu_spmm_apply(op, dX, t, dY, t, t) == 0, cu.pcu_last_error()
+            out[lean, t] = dev.down(dY, (m, t))
+            ref = Aext @ np.vstack([X, H])
+            assert np.allclose(out[lean, t], ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+            dev.free(dX, dY)
+        cu.pcu_spmm_destroy(op)
+    for t in (8, 16, 32):
+        assert np.array_equal(out["0", t], out["1", t])
 
 
 def test_spmm_long_rows_and_empty_rows(dev):
