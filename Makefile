@@ -19,7 +19,7 @@ CU_OBJS  := $(patsubst %.cu,$(OBJ)/%.o,$(CU_SRCS)) $(OBJ)/bj_symbolic.o
 H_SRCS   := pa_csr.c pa_operator.c pa_block_jacobi.c pa_ecg.c pa_driver.c
 H_OBJS   := $(patsubst %.c,$(OBJ)/%.o,$(H_SRCS))
 
-TARGETS := $(LIB)/libmpishim.so $(LIB)/libprealps_cuda.so $(LIB)/libprealps_b200.so
+TARGETS := $(LIB)/libmpishim.so $(LIB)/libprealps_cuda.so $(LIB)/libprealps_b200.so $(BIN)/bench_kernels
 ifneq ($(wildcard $(REF)/examples/test_ecg_prealps_op.c),)
 TARGETS += $(BIN)/test_ecg_prealps_op $(BIN)/test_ecg_bench_fused
 endif
@@ -55,6 +55,11 @@ $(BIN)/test_ecg_prealps_op: $(REF)/examples/test_ecg_prealps_op.c $(LIB)/libprea
 
 $(BIN)/test_ecg_bench_fused: $(REF)/examples/test_ecg_bench_fused.c $(LIB)/libprealps_b200.so | $(BIN)
 	$(CC) -O2 -std=gnu99 -w -Iinclude/compat -Iinclude -Impishim $< -o $@ -L$(LIB) -lprealps_b200 -lprealps_cuda \
+	    -lmpishim -Wl,-rpath,'$$ORIGIN/../lib' -lm
+
+# the preAlps half of the reference's test_bench_spmm.c / test_bench_bjacobi.c (those need PETSc)
+$(BIN)/bench_kernels: examples/bench_kernels.c $(LIB)/libprealps_b200.so | $(BIN)
+	$(CC) -O2 -std=gnu99 -Wall -Iinclude -Impishim $< -o $@ -L$(LIB) -lprealps_b200 -lprealps_cuda \
 	    -lmpishim -Wl,-rpath,'$$ORIGIN/../lib' -lm
 
 oracle:
