@@ -26,6 +26,19 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 METRIC = "ecg_t8_bjacobi_iterations_per_s"
 UNIT = "iterations/s"
+# --operator: (kind of preAlps_b200_OperatorBuildStencil, generator of oracle/gen_matrices.py for the CPU arm, description);
+# the default (BASELINE configs[1]) is the 7-point Poisson operator, the others serve configs[2..4]
+OPERATORS = {"poisson7": (0, lambda g, n: g.poisson7(n), "3D Poisson 7-point %d^3"),
+             "stencil27": (1, lambda g, n: g.stencil27(n), "3D 27-point stencil %d^3"),
+             "elasticity": (2, lambda g, n: g.elasticity3d(n, n, n), "3D Q1 linear elasticity %d^3 nodes x 3 dof")}
+
+
+def n_rows(operator, n):
+    return n ** 3 if operator != "elasticity" else 3 * n * n * (n - 1)  # the face x = 0 is clamped
+
+
+def metric_name(args):
+    return METRIC if args.t == 8 else "ecg_t%d_bjacobi_iterations_per_s" % args.t
 
 
 def measured_peaks():
@@ -92,17 +105,17 @@ def reference_arm(args, as_baseline=False):
         return None
     with tempfile.TemporaryDirectory() as d:
         mtx = os.path.join(d, "A.mtx")
-        gen_matrices.write_mtx(mtx, gen_matrices.poisson7(n_s))
+        gen_matrices.write_mtx(mtx, OPERATORS[args.operator][1](gen_matrices, n_s))
         env = dict(os.environ, MPISHIM_NP=str(args.nsub))
         t0 = time.time()
-        subprocess.run([exe, "-m", mtx, "-e", str(args.t), "-o", "0", "-r", "0", "-t", repr(args.tol), "-d", d, "-q"],
+        subprocess.run([exe, "-m", mtx, "-e", str(args.t), "-o", "0", "-r", str(args.bs_red), "-t", repr(args.tol), "-d", d, "-q"],
                        check=True, env=env, stdout=subprocess.DEVNULL)
         wall = time.time() - t0
         s = json.load(open(os.path.join(d, "summary.json")))
     it_s_sample = s["iter"] / s["t_solve"]
-    rows_ratio = float(n_s ** 3) / float(args.n ** 3)
+    rows_ratio = float(n_rows(args.operator, n_s)) / float(n_rows(args.operator, args.n))
     value = it_s_sample * rows_ratio
-    sample = ("poisson7 %d^3 (%.4g of the rows of %d^3), S=%d ranks x 1 thread (mpishim), t=%d, tol %g: %d iterations in %.2f s "
+    sample = (args.operator + " %d^3 (%.4g of the rows of %d^3), S=%d ranks x 1 thread (mpishim), t=%d, tol %g: %d iterations in %.2f s "
               "(SpMM %.2f s, block-Jacobi %.2f s; factorisation %.1f s not counted); iterations/s scaled by the row ratio, "
               "which favours the CPU (nnz(L) per row grows with the block size)"
               % (n_s, rows_ratio, args.n, args.nsub, args.t, args.tol, s["iter"], s["t_solve"], s["t_op"], s["t_prec"],
@@ -111,7 +124,7 @@ def reference_arm(args, as_baseline=False):
             "sample_iterations_per_s": it_s_sample, "sample_iterations": s["iter"], "wall_s": wall}
     if as_baseline:
         return base
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"metric": metric_name(args), "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args), "cpu_baseline": base,
@@ -120,9 +133,11 @@ def reference_arm(args, as_baseline=False):
 
 
 def workload_config(args):
-    return {"workload": "synthetic 3D Poisson 7-point %d^3 (%d rows), ECG t=%d + block Jacobi, %d METIS subdomains, tol %g"
-            % (args.n, args.n ** 3, args.t, args.nsub, args.tol),
-            "n": args.n, "t": args.t, "subdomains": args.nsub, "tol": args.tol, "ortho_alg": "ORTHODIR", "bs_red": "NO_BS_RED",
+    rows = n_rows(args.operator, args.n)
+    return {"workload": "synthetic " + OPERATORS[args.operator][2] % args.n + " (%d rows), ECG t=%d + block Jacobi, %d METIS "
+            "subdomains, tol %g" % (rows, args.t, args.nsub, args.tol),
+            "n": args.n, "t": args.t, "subdomains": args.nsub, "tol": args.tol, "ortho_alg": "ORTHODIR",
+            "bs_red": "ADAPT_BS (whole solves only; the K timed iterations run NO_BS_RED)" if args.bs_red else "NO_BS_RED",
             "l2": "inputs larger than L2 (factor + blocks ~17 GB per pass); per-kernel timings flush L2 between repetitions"}
 
 
@@ -145,6 +160,9 @@ def main():
     ap.add_argument("--enl", dest="t", type=int, default=8, help="enlarging factor t")
     ap.add_argument("--nsub", type=int, default=8, help="METIS subdomains = block-Jacobi blocks")
     ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--operator", default="poisson7", choices=sorted(OPERATORS))
+    ap.add_argument("--bs-red", type=int, default=0, choices=[0, 1], help="1 = ADAPT_BS in the whole solves (-r 1)")
+    ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--ref-n", type=int, default=64, help="grid size of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -209,7 +227,7 @@ def main():
 
     per = args.nsub // world
     t_setup = time.time()
-    assert capi.lib.preAlps_b200_OperatorBuildStencil(0, args.n, args.nsub, rank * per, (rank + 1) * per) == 0
+    assert capi.lib.preAlps_b200_OperatorBuildStencil(OPERATORS[args.operator][0], args.n, args.nsub, rank * per, (rank + 1) * per) == 0
     t_part = time.time() - t_setup
     assert capi.lib.preAlps_b200_BlockJacobiCreate() == 0
     t_setup = time.time() - t_setup
@@ -220,11 +238,11 @@ def main():
 
     # ---- e2e: whole solves through the RCI API with host buffers (the first one also warms everything up)
     barrier()
-    sol, hist, info0 = capi.solve(rhs, args.t, args.tol)
+    sol, hist, info0 = capi.solve(rhs, args.t, args.tol, max_iter=args.max_iter, bs_red=args.bs_red)
     tts_all = []
     for _ in range(3):  # median of three timed solves (each one: host rhs in, ~60 iterations, host solution out)
         barrier()
-        sol, hist, info = capi.solve(rhs, args.t, args.tol)
+        sol, hist, info = capi.solve(rhs, args.t, args.tol, max_iter=args.max_iter, bs_red=args.bs_red)
         barrier()
         tts_all.append(max_over_ranks(info.t_solve))
     tts = sorted(tts_all)[1]
@@ -276,7 +294,7 @@ def main():
             except Exception as e:  # the baseline must never take the GPU line down
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": UNIT,
