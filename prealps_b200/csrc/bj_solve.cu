@@ -33,7 +33,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- forward right-hand-side assembly: one group of G lanes per column
-template <int T>
+// PREFETCH (opt-in, PREALPS_BJ_ASM_PREFETCH=1; written after the last GPU session of round 1, not measured yet): a
+// group's FIRST column fetches everything static -- its forest column, the row of the caller's block it maps to, its
+// gather range and the first 8 gather indices -- BEFORE griddepcontrol.wait, i.e. while the previous level's forward
+// sweep drains; only the loads of B and U (data written earlier in the stream) come after the wait.  An assemble launch
+// above level 0 moves ~10 MB and is a chain of 4 dependent round trips; this takes 3 of them off the critical path.
+template <int T, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads) assemble_kernel(const int* __restrict__ cols, int ncols,
                                                             const double* __restrict__ B, int ldb, int t,
                                                             const int* __restrict__ perm,
@@ -45,22 +50,35 @@ __global__ void __launch_bounds__(kThreads) assemble_kernel(const int* __restric
   const int gid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / G);
   const int lig = threadIdx.x % G;
   const int ngroups = (int)((long long)gridDim.x * blockDim.x / G);
+  int c_first = 0, row_first = 0;
+  long long g_first = 0, g1_first = 0;
+  long long idx_first[8];
+  if (PREFETCH && gid < ncols) {
+    c_first = __ldg(cols + gid);
+    row_first = __ldg(perm + c_first);
+    g_first = __ldg(gl_ptr + c_first);
+    g1_first = __ldg(gl_ptr + c_first + 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) idx_first[j] = (g_first + j < g1_first) ? __ldg(gl_idx + g_first + j) : -1;
+  }
   pdl_wait();
   pdl_launch_dependents();
   for (int q = gid; q < ncols; q += ngroups) {
-    const int c = cols[q];
-    const double* src = B + (size_t)perm[c] * ldb;
+    const bool pre = PREFETCH && q == gid;
+    const int c = pre ? c_first : cols[q];
+    const double* src = B + (size_t)(pre ? row_first : perm[c]) * ldb;
     double a0 = 0.0, a1 = 0.0;
     const int c0 = CPL * lig;
     if (c0 < t) a0 = src[c0];
     if (CPL == 2 && c0 + 1 < t) a1 = src[c0 + 1];
     // the list is walked in order (fixed summation order); 8 slots are fetched at a time so the loads overlap
-    const long long g1 = gl_ptr[c + 1];
-    for (long long g = gl_ptr[c]; g < g1; g += 8) {
+    const long long g0 = pre ? g_first : gl_ptr[c];
+    const long long g1 = pre ? g1_first : gl_ptr[c + 1];
+    for (long long g = g0; g < g1; g += 8) {
       long long idx[8];
       double2 v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) idx[j] = (g + j < g1) ? __ldg(gl_idx + g + j) : -1;
+      for (int j = 0; j < 8; ++j) idx[j] = (pre && g == g0) ? idx_first[j] : ((g + j < g1) ? __ldg(gl_idx + g + j) : -1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[j] = make_double2(0.0, 0.0);
@@ -539,6 +557,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   pcu_ctx* c = bj->ctx;
   cudaStream_t st = c->stream;
   LevelProfiler prof(st);
+  const bool asm_prefetch = getenv("PREALPS_BJ_ASM_PREFETCH") != nullptr;  // read per apply: tests flip it in-process
   constexpr int G = (T >= 2) ? T / 2 : 1;
   SweepArgs a{};
   a.Wk = bj->Wk; a.Y = bj->Y; a.U = bj->U; a.Xp = bj->Xp; a.rows = bj->rows; a.perm = bj->perm;
@@ -549,8 +568,12 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
     if (ncols > 0) {
       prof.mark("asm L" + std::to_string(l) + " cols=" + std::to_string(ncols), 3.0 * ncols * T * 8);
       const int grid = stream_grid(c, (long long)ncols * G, kThreads, 8);
-      launch_chain(assemble_kernel<T>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t, bj->perm,
-                   bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
+      if (asm_prefetch)
+        launch_chain(assemble_kernel<T, true>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t,
+                     bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
+      else
+        launch_chain(assemble_kernel<T, false>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t,
+                     bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
       PCU_LAUNCH_CHECK(c);
     }
     const int nu = bj->fwd_unit_ptr[l + 1] - bj->fwd_unit_ptr[l];

@@ -238,6 +238,39 @@ def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t):
     cu.pcu_bj_destroy(bj)
 
 
+@candidates
+@pytest.mark.parametrize("t", [1, 8, 16])
+def test_block_jacobi_assemble_prefetch_candidate_is_bit_identical(dev, t, monkeypatch):
+    """PREALPS_BJ_ASM_PREFETCH=1 only moves loads of static data in front of griddepcontrol.wait: same bits"""
+    A = gen_matrices.poisson7(20).tocsr()
+    n = A.shape[0]
+    cuts = np.array([0, n // 2, n], dtype=np.int32)
+    keep = []
+    for b in range(2):
+        U = sp.triu(A[cuts[b]:cuts[b + 1], cuts[b]:cuts[b + 1]], format="csr")
+        U.sort_indices()
+        keep.append((U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data.copy()))
+    rp = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[0]) for k in keep])
+    ci = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[1]) for k in keep])
+    vv = (C.POINTER(C.c_double) * 2)(*[capi.dp(k[2]) for k in keep])
+    bj = C.c_void_p()
+    assert cu.pcu_bj_create(dev.ctx, 2, capi.ip(cuts), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
+    B = np.random.default_rng(t).standard_normal((n, t))
+    dB, dX = dev.up(B), dev.zeros(n * t)
+    out = []
+    for flag in (None, "1", None, "1"):
+        if flag is None:
+            monkeypatch.delenv("PREALPS_BJ_ASM_PREFETCH", raising=False)
+        else:
+            monkeypatch.setenv("PREALPS_BJ_ASM_PREFETCH", flag)
+        assert cu.pcu_bj_apply(bj, dB, t, dX, t, t) == 0, cu.pcu_last_error()
+        out.append(dev.down(dX, (n, t)))
+    for o in out[1:]:
+        assert np.array_equal(o, out[0])
+    dev.free(dB, dX)
+    cu.pcu_bj_destroy(bj)
+
+
 def test_block_jacobi_long_panels_cut_across_ctas(dev):
     """a block large enough for separators beyond 1024 columns: exercises the inter-CTA split of long panels"""
     import scipy.sparse.linalg as spla
