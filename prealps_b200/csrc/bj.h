@@ -101,4 +101,12 @@ struct pcu_bj {
   double* scratch = nullptr;
   int* counters = nullptr;
   int scratch_slots = 0, ncounters = 0;
+  // opt-in (PREALPS_BJ_GRAPH=1): the launch chain of one apply, captured once per argument tuple and replayed
+  struct ApplyGraph {
+    const double* B; int ldb; double* X; int ldx; int t;
+    cudaGraphExec_t exec;   // nullptr: tuple seen once, captured on its next use
+    long long kernels;      // launches the chain contains (added to the context's launch counter on every replay)
+  };
+  std::vector<ApplyGraph> graphs;
+  bool graph_failed = false;  // a capture or instantiation failed: plain launches from then on
 };

@@ -354,6 +354,8 @@ int pcu_bj_destroy(pcu_bj* bj) {
   if (!bj) return 0;
   cudaSetDevice(bj->ctx->device);
   cudaStreamSynchronize(bj->ctx->stream);
+  for (auto& g : bj->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   cudaFree(bj->fwd_data); cudaFree(bj->bwd_data); cudaFree(bj->fwd_panels); cudaFree(bj->bwd_panels);
   cudaFree(bj->fwd_units); cudaFree(bj->bwd_units); cudaFree(bj->perm); cudaFree(bj->rows);
   cudaFree(bj->lvl_cols); cudaFree(bj->gl_ptr); cudaFree(bj->gl_idx);

@@ -448,6 +448,9 @@ int ensure_work(pcu_bj* bj, int T) {
   if (bj->cap_t >= T) return 0;
   pcu_ctx* c = bj->ctx;
   PCU_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& g : bj->graphs)  // the captured chains point into the work vectors that are about to move
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  bj->graphs.clear();
   cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp);
   bj->Wk = bj->Y = bj->U = bj->Xp = nullptr;
   cudaFree(bj->scratch); cudaFree(bj->counters);
@@ -617,16 +620,10 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   return 0;
 }
 
-}  // namespace
-
-extern "C" int pcu_bj_apply(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
-  PCU_CHECK(bj && B && X && t >= 1 && t <= 32, "pcu_bj_apply: bad arguments (t=%d, need 1..32)", t);
-  PCU_CHECK(ldb >= t && ldx >= t, "pcu_bj_apply: leading dimension smaller than t");
-  const int T = pick_T(t);
-  if (ensure_work(bj, T)) return 1;
+int dispatch_apply(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   // the work vectors are laid out for cap_t columns; a narrower solve uses its own T, which is
   // consistent within one apply (every vector is rewritten before it is read)
-  switch (T) {
+  switch (pick_T(t)) {
     case 1: return apply_T<1>(bj, B, ldb, X, ldx, t);
     case 2: return apply_T<2>(bj, B, ldb, X, ldx, t);
     case 4: return apply_T<4>(bj, B, ldb, X, ldx, t);
@@ -634,4 +631,66 @@ extern "C" int pcu_bj_apply(pcu_bj* bj, const double* B, int ldb, double* X, int
     case 16: return apply_T<16>(bj, B, ldb, X, ldx, t);
     default: return apply_T<32>(bj, B, ldb, X, ldx, t);
   }
+}
+
+// PREALPS_BJ_GRAPH=1 (opt-in; written after the last GPU session of round 1, not measured yet): the ~60 launches of an
+// apply are captured into a CUDA graph (the programmatic-dependent-launch attributes become programmatic edges) the
+// second time an argument tuple (B, ldb, X, ldx, t) is seen, and replayed with one cudaGraphLaunch afterwards.  ECG
+// rotates a handful of block pointers, so a few graphs cover a solve.  Aimed at one subdomain per GPU, where a level
+// is a few tens of microseconds and the chain is bound by launch latency.
+constexpr size_t kMaxGraphs = 32;
+
+int apply_graphed(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
+  pcu_ctx* c = bj->ctx;
+  for (auto& g : bj->graphs) {
+    if (g.B != B || g.ldb != ldb || g.X != X || g.ldx != ldx || g.t != t) continue;
+    if (g.exec) {
+      PCU_CUDA(cudaGraphLaunch(g.exec, c->stream));
+      c->launches += g.kernels;
+      return 0;
+    }
+    // second use of this tuple: capture the chain
+    const int64_t l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
+    const int rc = dispatch_apply(bj, B, ldb, X, ldx, t);
+    const cudaError_t e_end = cudaStreamEndCapture(c->stream, &graph);
+    const int64_t nk = c->launches - l0;
+    c->launches = l0;
+    cudaGraphExec_t exec = nullptr;
+    if (rc != 0 || e_end != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      break;
+    }
+    cudaGraphDestroy(graph);
+    g.exec = exec;
+    g.kernels = nk;
+    PCU_CUDA(cudaGraphLaunch(g.exec, c->stream));
+    c->launches += g.kernels;
+    return 0;
+  }
+  const bool known = [&] {
+    for (auto& g : bj->graphs)
+      if (g.B == B && g.ldb == ldb && g.X == X && g.ldx == ldx && g.t == t) return true;
+    return false;
+  }();
+  if (known) {  // fell out of the loop: capture failed
+    cudaGetLastError();
+    bj->graph_failed = true;
+    set_error("pcu_bj_apply: CUDA graph capture of the apply chain failed, using plain launches");
+  } else if (bj->graphs.size() < kMaxGraphs) {
+    bj->graphs.push_back(pcu_bj::ApplyGraph{B, ldb, X, ldx, t, nullptr, 0});
+  }
+  return dispatch_apply(bj, B, ldb, X, ldx, t);
+}
+
+}  // namespace
+
+extern "C" int pcu_bj_apply(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
+  PCU_CHECK(bj && B && X && t >= 1 && t <= 32, "pcu_bj_apply: bad arguments (t=%d, need 1..32)", t);
+  PCU_CHECK(ldb >= t && ldx >= t, "pcu_bj_apply: leading dimension smaller than t");
+  if (ensure_work(bj, pick_T(t))) return 1;
+  if (!bj->graph_failed && getenv("PREALPS_BJ_GRAPH") != nullptr && getenv("PREALPS_BJ_PROFILE") == nullptr)
+    return apply_graphed(bj, B, ldb, X, ldx, t);
+  return dispatch_apply(bj, B, ldb, X, ldx, t);
 }

@@ -239,9 +239,11 @@ def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t):
 
 
 @candidates
+@pytest.mark.parametrize("var", ["PREALPS_BJ_ASM_PREFETCH", "PREALPS_BJ_GRAPH"])
 @pytest.mark.parametrize("t", [1, 8, 16])
-def test_block_jacobi_assemble_prefetch_candidate_is_bit_identical(dev, t, monkeypatch):
-    """PREALPS_BJ_ASM_PREFETCH=1 only moves loads of static data in front of griddepcontrol.wait: same bits"""
+def test_block_jacobi_candidates_are_bit_identical(dev, t, var, monkeypatch):
+    """PREALPS_BJ_ASM_PREFETCH=1 only moves loads of static data in front of griddepcontrol.wait; PREALPS_BJ_GRAPH=1 replays
+    the same launch chain from a CUDA graph (captured on the second use of an argument tuple): same bits"""
     A = gen_matrices.poisson7(20).tocsr()
     n = A.shape[0]
     cuts = np.array([0, n // 2, n], dtype=np.int32)
@@ -258,11 +260,11 @@ def test_block_jacobi_assemble_prefetch_candidate_is_bit_identical(dev, t, monke
     B = np.random.default_rng(t).standard_normal((n, t))
     dB, dX = dev.up(B), dev.zeros(n * t)
     out = []
-    for flag in (None, "1", None, "1"):
+    for flag in (None, "1", "1", "1", None, "1"):
         if flag is None:
-            monkeypatch.delenv("PREALPS_BJ_ASM_PREFETCH", raising=False)
+            monkeypatch.delenv(var, raising=False)
         else:
-            monkeypatch.setenv("PREALPS_BJ_ASM_PREFETCH", flag)
+            monkeypatch.setenv(var, flag)
         assert cu.pcu_bj_apply(bj, dB, t, dX, t, t) == 0, cu.pcu_last_error()
         out.append(dev.down(dX, (n, t)))
     for o in out[1:]:
