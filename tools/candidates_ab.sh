@@ -1,0 +1,27 @@
+#!/bin/bash
+# tools/candidates_ab.sh -- first GPU call of the next round: the opt-in kernels written after the last GPU session of
+# round 1 (none of them has run on a B200 yet), each against the default, all in ONE gpurun call on one GPU:
+#     gpurun --timeout 900 -- 'bash tools/candidates_ab.sh'
+# 1. parity of the candidates (bit-identical to the defaults), 2. A/B timings.  Whatever wins becomes the default
+# (and its environment switch is inverted or dropped); whatever loses is deleted and recorded under profiles/.
+set -u
+out=gpurun_out
+mkdir -p $out
+PREALPS_TEST_CANDIDATES=1 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_ecg.py -q -m gpu -k "candidate or harness" \
+    > $out/cand_tests.log 2>&1
+echo "candidate tests rc=$?" | tee -a $out/cand_tests.log
+# SpMM: default vs lean row phase (27-point and 7-point 128^3, t = 1..32; only t >= 8 differ)
+python tools/spmm_sweep.py 128 > $out/cand_spmm_default.jsonl 2> $out/cand_spmm_default.err
+PREALPS_SPMM_LEAN=1 python tools/spmm_sweep.py 128 > $out/cand_spmm_lean.jsonl 2> $out/cand_spmm_lean.err
+# block-Jacobi apply, 8 subdomains of 64^3 on this GPU (the N=1 bench) and ONE 64^3 subdomain (what each GPU holds at N=8)
+for sub in 8 1; do
+  n=128; [ $sub = 1 ] && n=64
+  for v in "" "PREALPS_BJ_ASM_PREFETCH=1" "PREALPS_BJ_GRAPH=1" "PREALPS_BJ_ASM_PREFETCH=1 PREALPS_BJ_GRAPH=1"; do
+    echo "== n=$n subdomains=$sub $v" >> $out/cand_bj.log
+    env SUBDOMAINS=$sub $v python tools/profile_apply.py $n 1 20 8 >> $out/cand_bj.log 2>&1
+  done
+done
+# whole iterations with everything on
+python bench.py --no-cpu-baseline > $out/cand_bench_default.json 2> $out/cand_bench_default.err
+PREALPS_SPMM_LEAN=1 PREALPS_BJ_ASM_PREFETCH=1 PREALPS_BJ_GRAPH=1 python bench.py --no-cpu-baseline > $out/cand_bench_all.json 2> $out/cand_bench_all.err
+tail -n 3 $out/cand_tests.log; cat $out/cand_bj.log | grep -v METIS | tail -n 20

@@ -1,5 +1,7 @@
 """tools/profile_apply.py -- small driver for ncu: build the bench operator, then run a few calls of one kernel class.
     python tools/profile_apply.py [n] [what: 0 spmm | 1 block-Jacobi | 2 dense | 3 iterations] [reps] [t]
+STENCIL=0|1|2 picks the operator, SUBDOMAINS=S the number of METIS subdomains (default 8; SUBDOMAINS=1 with n=64 is what one
+GPU of an 8-GPU run of the 128^3 problem holds).
 """
 import ctypes as C
 import os
@@ -13,7 +15,8 @@ what = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 t = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 kind = int(os.environ.get("STENCIL", "0"))
-assert capi.lib.preAlps_b200_OperatorBuildStencil(kind, n, 8, 0, 8) == 0
+S = int(os.environ.get("SUBDOMAINS", "8"))
+assert capi.lib.preAlps_b200_OperatorBuildStencil(kind, n, S, 0, S) == 0
 if what != 0:
     assert capi.lib.preAlps_b200_BlockJacobiCreate() == 0
 ms = C.c_float()
