@@ -152,8 +152,13 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
 // halo row" and the row stride into ONE 64-bit byte offset relative to X, stored next to the value, so the row phase
 // is LDS.128 + 64-bit add + LDG + CPL DFMA per entry.  Needs ldx == T (rows of X and of the halo buffer are both
 // T doubles apart) and every row block of shape 0 within the staging capacity.
-template <int T, int CPL>
-__global__ void __launch_bounds__(kThreads) spmm_lean_kernel(SpmmArgs a) {
+// NB > 1 (PREALPS_SPMM_LEAN=2 or 4): the gathers of NB consecutive entries of a row are issued back to back before
+// their FMAs (which keep their order).  ptxas only schedules them that way when __launch_bounds__ names a minimum
+// number of CTAs per SM (MINB): with the bare (256) bound it aims at 32 registers / full occupancy and sinks every load
+// next to its consumer -- one gather in flight per lane, which is also what spmm_kernel does.  NB = 2: <= 48 registers,
+// 5 CTAs/SM; NB = 4: <= 64 registers, 4 CTAs/SM.
+template <int T, int CPL, int NB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) spmm_lean_kernel(SpmmArgs a) {
   static_assert(CPL == 2 || CPL == 4, "lanes own 2 or 4 adjacent columns");
   constexpr int G = T / CPL;
   constexpr int NG = kThreads / G;
@@ -182,8 +187,32 @@ __global__ void __launch_bounds__(kThreads) spmm_lean_kernel(SpmmArgs a) {
     double acc[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) acc[j] = 0.0;
+    int p = b;
+    if constexpr (NB > 1) {
+      for (; p + NB <= e; p += NB) {
+        double2 en[NB];
+        double x[NB][4];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) en[k] = s_ent[p + k];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const double* src = reinterpret_cast<const double*>(xl + __double_as_longlong(en[k].y));
+          if constexpr (CPL == 4) {
+            ldg4(src, x[k]);
+          } else {
+            const double2 v = ldg2(src);
+            x[k][0] = v.x;
+            x[k][1] = v.y;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) acc[j] = fma(en[k].x, x[k][j], acc[j]);
+      }
+    }
 #pragma unroll 4
-    for (int p = b; p < e; ++p) {
+    for (; p < e; ++p) {
       const double2 en = s_ent[p];
       const double* src = reinterpret_cast<const double*>(xl + __double_as_longlong(en.y));
       if constexpr (CPL == 4) {
@@ -206,10 +235,17 @@ __global__ void __launch_bounds__(kThreads) spmm_lean_kernel(SpmmArgs a) {
   }
 }
 
+template <int T, int CPL>
+void launch_lean_nb(const SpmmArgs& a, int nblk, int nb, cudaStream_t st) {
+  if (nb >= 4) spmm_lean_kernel<T, CPL, 4, 4><<<nblk, kThreads, 0, st>>>(a);
+  else if (nb >= 2) spmm_lean_kernel<T, CPL, 2, 5><<<nblk, kThreads, 0, st>>>(a);
+  else spmm_lean_kernel<T, CPL, 1, 0><<<nblk, kThreads, 0, st>>>(a);  // MINB = 0: same as the bare bound
+}
+
 template <int T>
-void launch_lean(const SpmmArgs& a, int nblk, bool wide, cudaStream_t st) {
-  if (wide) spmm_lean_kernel<T, 4><<<nblk, kThreads, 0, st>>>(a);
-  else spmm_lean_kernel<T, 2><<<nblk, kThreads, 0, st>>>(a);
+void launch_lean(const SpmmArgs& a, int nblk, bool wide, int nb, cudaStream_t st) {
+  if (wide) launch_lean_nb<T, 4>(a, nblk, nb, st);
+  else launch_lean_nb<T, 2>(a, nblk, nb, st);
 }
 
 // any 1 <= t <= 32: 16 lanes per row, lane owns columns lig and lig+16
@@ -284,7 +320,8 @@ struct pcu_spmm {
   double* d_val = nullptr;
   int4* d_blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
   int nblk[2] = {0, 0};
-  bool lean = false;  // PREALPS_SPMM_LEAN=1 and every shape-0 row block fits the staging buffer: spmm_lean_kernel from t = 8 up
+  int lean = 0;  // PREALPS_SPMM_LEAN=1|2|4 (gathers in flight per lane) and every shape-0 row block fits the staging
+                 // buffer: spmm_lean_kernel from t = 8 up
   // halo
   int nnbr = 0;
   std::vector<int> nbr_rank, send_ptr, recv_ptr;
@@ -338,9 +375,9 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
     op->nblk[sh] = (int)blk[sh].size();
   }
   if (const char* e = getenv("PREALPS_SPMM_LEAN")) {
-    op->lean = atoi(e) != 0;
+    op->lean = std::max(0, atoi(e));
     for (const int4& b : blk[0])
-      if (b.w - b.z > kShapeNnz[0]) op->lean = false;
+      if (b.w - b.z > kShapeNnz[0]) op->lean = 0;
   }
   PCU_CUDA(cudaMalloc(&op->d_rowPtr, sizeof(int) * (size_t)(m + 1)));
   PCU_CUDA(cudaMalloc(&op->d_colInd, sizeof(int) * (size_t)std::max<int64_t>(op->nnz, 1)));
@@ -437,11 +474,11 @@ int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, i
   // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
   const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
                     ((uintptr_t)op->d_halo % 32 == 0) && op->nnz <= 12 * (int64_t)op->m;
-  const bool lean = op->lean && aligned && pow2 && t >= 8 && ldx == t;
+  const bool lean = op->lean > 0 && aligned && pow2 && t >= 8 && ldx == t;
   if (lean) {
-    if (t == 8) launch_lean<8>(a, nblk, wide, c->stream);
-    else if (t == 16) launch_lean<16>(a, nblk, wide, c->stream);
-    else launch_lean<32>(a, nblk, wide, c->stream);
+    if (t == 8) launch_lean<8>(a, nblk, wide, op->lean, c->stream);
+    else if (t == 16) launch_lean<16>(a, nblk, wide, op->lean, c->stream);
+    else launch_lean<32>(a, nblk, wide, op->lean, c->stream);
   } else if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {

@@ -64,7 +64,8 @@ candidates = pytest.mark.skipif(not os.environ.get("PREALPS_TEST_CANDIDATES"),
 @candidates
 @pytest.mark.parametrize("gen,N", [("poisson7", 14), ("stencil27", 9)])
 def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
-    """PREALPS_SPMM_LEAN=1 (spmm_lean_kernel) keeps the mapping and the summation order: same bits as the default kernel"""
+    """PREALPS_SPMM_LEAN=1|2|4 (spmm_lean_kernel, 1, 2 or 4 gathers in flight per lane) keeps the mapping and the summation
+    order: same bits as the default kernel"""
     A = getattr(gen_matrices, gen)(N).tocsr()
     m = A.shape[0]
     nh = 53
@@ -73,7 +74,7 @@ def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
     Aext.sort_indices()
     rng = np.random.default_rng(1)
     out = {}
-    for lean in ("0", "1"):
+    for lean in ("0", "1", "2", "4"):
         monkeypatch.setenv("PREALPS_SPMM_LEAN", lean)
         op = C.c_void_p()
         assert cu.pcu_spmm_create(dev.ctx, m, nh, capi.ip(Aext.indptr.astype(np.int32)), capi.ip(Aext.indices.astype(np.int32)),
@@ -94,7 +95,8 @@ def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
             dev.free(dX, dY)
         cu.pcu_spmm_destroy(op)
     for t in (8, 16, 32):
-        assert np.array_equal(out["0", t], out["1", t])
+        for lean in ("1", "2", "4"):
+            assert np.array_equal(out["0", t], out[lean, t])
 
 
 def test_spmm_long_rows_and_empty_rows(dev):

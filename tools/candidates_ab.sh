@@ -12,7 +12,9 @@ PREALPS_TEST_CANDIDATES=1 timeout 600 python -m pytest tests/test_gpu_kernels.py
 echo "candidate tests rc=$?" | tee -a $out/cand_tests.log
 # SpMM: default vs lean row phase (27-point and 7-point 128^3, t = 1..32; only t >= 8 differ)
 python tools/spmm_sweep.py 128 > $out/cand_spmm_default.jsonl 2> $out/cand_spmm_default.err
-PREALPS_SPMM_LEAN=1 python tools/spmm_sweep.py 128 > $out/cand_spmm_lean.jsonl 2> $out/cand_spmm_lean.err
+for nb in 1 2 4; do  # gathers in flight per lane
+  PREALPS_SPMM_LEAN=$nb python tools/spmm_sweep.py 128 > $out/cand_spmm_lean$nb.jsonl 2> $out/cand_spmm_lean$nb.err
+done
 # block-Jacobi apply, 8 subdomains of 64^3 on this GPU (the N=1 bench) and ONE 64^3 subdomain (what each GPU holds at N=8)
 for sub in 8 1; do
   n=128; [ $sub = 1 ] && n=64
@@ -24,4 +26,4 @@ done
 # whole iterations with everything on
 python bench.py --no-cpu-baseline > $out/cand_bench_default.json 2> $out/cand_bench_default.err
 PREALPS_SPMM_LEAN=1 PREALPS_BJ_ASM_PREFETCH=1 PREALPS_BJ_GRAPH=1 python bench.py --no-cpu-baseline > $out/cand_bench_all.json 2> $out/cand_bench_all.err
-tail -n 3 $out/cand_tests.log; cat $out/cand_bj.log | grep -v METIS | tail -n 20
+grep -h '"t": 8,' $out/cand_spmm_*.jsonl; tail -n 3 $out/cand_tests.log; cat $out/cand_bj.log | grep -v METIS | tail -n 20
