@@ -62,8 +62,9 @@ inline int stream_grid(const pcu_ctx* ctx, int64_t work_items, int per_block, in
 int ensure_partials(pcu_ctx* ctx, size_t doubles);
 
 // NCCL thin wrappers (ctx.cu)
-int nccl_send(pcu_ctx* ctx, const void* buf, size_t count, int is_double, int peer);
-int nccl_recv(pcu_ctx* ctx, void* buf, size_t count, int is_double, int peer);
+// st == nullptr: the library stream
+int nccl_send(pcu_ctx* ctx, const void* buf, size_t count, int is_double, int peer, cudaStream_t st = nullptr);
+int nccl_recv(pcu_ctx* ctx, void* buf, size_t count, int is_double, int peer, cudaStream_t st = nullptr);
 int nccl_group_start(pcu_ctx* ctx);
 int nccl_group_end(pcu_ctx* ctx);
 

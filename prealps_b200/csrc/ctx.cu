@@ -68,12 +68,12 @@ static int load_nccl() {
     if (r_ != 0) { set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); return 1; } \
   } while (0)
 
-int nccl_send(pcu_ctx* ctx, const void* buf, size_t count, int is_double, int peer) {
-  PCU_NCCL(g_nccl.Send(buf, count, is_double ? kNcclFloat64 : kNcclInt32, peer, ctx->nccl_comm, ctx->stream));
+int nccl_send(pcu_ctx* ctx, const void* buf, size_t count, int is_double, int peer, cudaStream_t st) {
+  PCU_NCCL(g_nccl.Send(buf, count, is_double ? kNcclFloat64 : kNcclInt32, peer, ctx->nccl_comm, st ? st : ctx->stream));
   return 0;
 }
-int nccl_recv(pcu_ctx* ctx, void* buf, size_t count, int is_double, int peer) {
-  PCU_NCCL(g_nccl.Recv(buf, count, is_double ? kNcclFloat64 : kNcclInt32, peer, ctx->nccl_comm, ctx->stream));
+int nccl_recv(pcu_ctx* ctx, void* buf, size_t count, int is_double, int peer, cudaStream_t st) {
+  PCU_NCCL(g_nccl.Recv(buf, count, is_double ? kNcclFloat64 : kNcclInt32, peer, ctx->nccl_comm, st ? st : ctx->stream));
   return 0;
 }
 int nccl_group_start(pcu_ctx*) { PCU_NCCL(g_nccl.GroupStart()); return 0; }

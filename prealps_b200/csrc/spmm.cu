@@ -309,19 +309,95 @@ __global__ void halo_pack_kernel(const double* __restrict__ X, int ldx, int t, c
   }
 }
 
+// Overlapped product (opt-in, PREALPS_SPMM_OVERLAP=1): Y[r, :] += sum_k hval[k] * H[hcol[k], :] for the rows that read
+// halo rows, after the local kernel has written the partial sums of the entries with column < m.  Halo columns sort
+// after the local ones, so continuing each row's FMA chain from the stored partial sum reproduces the merged kernel's
+// summation order bit for bit.  16 lanes per row, lane owns columns lig and lig + 16 (any t <= 32).
+__global__ void __launch_bounds__(kThreads) halo_add_kernel(int nb, const int* __restrict__ brow, const int* __restrict__ hptr,
+                                                            const int* __restrict__ hcol, const double* __restrict__ hval,
+                                                            const double* __restrict__ H, int t, double* Y, int ldy) {
+  constexpr int G = 16;
+  const int gid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / G), lig = threadIdx.x % G;
+  const int ngroups = (int)((long long)gridDim.x * blockDim.x / G);
+  for (int q = gid; q < nb; q += ngroups) {
+    double* y = Y + (size_t)brow[q] * ldy;
+    const int b = hptr[q], e = hptr[q + 1];
+    double acc0 = (lig < t) ? y[lig] : 0.0, acc1 = (lig + 16 < t) ? y[lig + 16] : 0.0;
+    for (int p = b; p < e; ++p) {
+      const double v = hval[p];
+      const double* src = H + (size_t)hcol[p] * t;
+      if (lig < t) acc0 = fma(v, __ldg(src + lig), acc0);
+      if (lig + 16 < t) acc1 = fma(v, __ldg(src + lig + 16), acc1);
+    }
+    if (lig < t) y[lig] = acc0;
+    if (lig + 16 < t) y[lig + 16] = acc1;
+  }
+}
+
+// one CSR on the device with its row blocks
+struct CsrDev {
+  int* rowPtr = nullptr;
+  int* colInd = nullptr;
+  double* val = nullptr;
+  int4* blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
+  int nblk[2] = {0, 0};
+  int64_t nnz = 0;
+  bool fits0 = true;  // every shape-0 row block fits the staging buffer (spmm_lean_kernel needs that)
+};
+
+int upload_csr(int m, const int* rowPtr, const int* colInd, const double* val, CsrDev* d) {
+  d->nnz = rowPtr[m];
+  // row blocks: <= kRowCap rows and <= kNnzCap entries; an over-long row gets a block of its own
+  std::vector<int4> blk[2];
+  for (int sh = 0; sh < 2; ++sh) {
+    for (int r = 0; r < m;) {
+      int e = r;
+      while (e < m && e - r < kShapeRows[sh] && rowPtr[e + 1] - rowPtr[r] <= kShapeNnz[sh]) ++e;
+      if (e == r) e = r + 1;
+      blk[sh].push_back(make_int4(r, e, rowPtr[r], rowPtr[e]));
+      r = e;
+    }
+    d->nblk[sh] = (int)blk[sh].size();
+  }
+  for (const int4& b : blk[0])
+    if (b.w - b.z > kShapeNnz[0]) d->fits0 = false;
+  PCU_CUDA(cudaMalloc(&d->rowPtr, sizeof(int) * (size_t)(m + 1)));
+  PCU_CUDA(cudaMalloc(&d->colInd, sizeof(int) * (size_t)std::max<int64_t>(d->nnz, 1)));
+  PCU_CUDA(cudaMalloc(&d->val, sizeof(double) * (size_t)std::max<int64_t>(d->nnz, 1)));
+  for (int sh = 0; sh < 2; ++sh) PCU_CUDA(cudaMalloc(&d->blk[sh], sizeof(int4) * std::max<size_t>(blk[sh].size(), 1)));
+  PCU_CUDA(cudaMemcpy(d->rowPtr, rowPtr, sizeof(int) * (size_t)(m + 1), cudaMemcpyHostToDevice));
+  PCU_CUDA(cudaMemcpy(d->colInd, colInd, sizeof(int) * (size_t)d->nnz, cudaMemcpyHostToDevice));
+  PCU_CUDA(cudaMemcpy(d->val, val, sizeof(double) * (size_t)d->nnz, cudaMemcpyHostToDevice));
+  for (int sh = 0; sh < 2; ++sh)
+    if (!blk[sh].empty())
+      PCU_CUDA(cudaMemcpy(d->blk[sh], blk[sh].data(), sizeof(int4) * blk[sh].size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void free_csr(CsrDev* d) {
+  cudaFree(d->rowPtr); cudaFree(d->colInd); cudaFree(d->val); cudaFree(d->blk[0]); cudaFree(d->blk[1]);
+  *d = CsrDev();
+}
+
 }  // namespace
 
 struct pcu_spmm {
   pcu_ctx* ctx = nullptr;
   int m = 0, nhalo = 0;
   int64_t nnz = 0;
-  int* d_rowPtr = nullptr;
-  int* d_colInd = nullptr;
-  double* d_val = nullptr;
-  int4* d_blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
-  int nblk[2] = {0, 0};
-  int lean = 0;  // PREALPS_SPMM_LEAN=1|2|4 (gathers in flight per lane) and every shape-0 row block fits the staging
-                 // buffer: spmm_lean_kernel from t = 8 up
+  CsrDev A;           // the local row panel, columns >= m read the halo buffer
+  int lean = 0;       // PREALPS_SPMM_LEAN=1|2|4 (gathers in flight per lane): spmm_lean_kernel from t = 8 up
+  // PREALPS_SPMM_OVERLAP=1 and nhalo > 0: the panel split into its entries with column < m (Aloc, same rows) and the halo
+  // entries of the boundary rows; the halo exchange then runs on comm_stream next to the local kernel
+  bool overlap = false;
+  CsrDev Aloc;
+  int nbrow = 0;
+  int* d_brow = nullptr;   // boundary rows, ascending
+  int* d_hptr = nullptr;   // nbrow + 1
+  int* d_hcol = nullptr;   // halo row (column - m)
+  double* d_hval = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_x = nullptr, ev_h = nullptr;
   // halo
   int nnbr = 0;
   std::vector<int> nbr_rank, send_ptr, recv_ptr;
@@ -338,6 +414,7 @@ static int ensure_halo_buffers(pcu_spmm* op, int t) {
   if (op->buf_t >= t) return 0;
   pcu_ctx* c = op->ctx;
   PCU_CUDA(cudaStreamSynchronize(c->stream));
+  if (op->comm_stream) PCU_CUDA(cudaStreamSynchronize(op->comm_stream));
   if (op->d_sendbuf) cudaFree(op->d_sendbuf);
   if (op->d_halo) cudaFree(op->d_halo);
   op->d_sendbuf = op->d_halo = nullptr;
@@ -362,33 +439,38 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
   for (int64_t p = 0; p < op->nnz; ++p)
     PCU_CHECK(colInd[p] >= 0 && colInd[p] < m + nhalo, "pcu_spmm_create: column index %d out of range at %lld",
               colInd[p], (long long)p);
-  // row blocks: <= kRowCap rows and <= kNnzCap entries; an over-long row gets a block of its own
-  std::vector<int4> blk[2];
-  for (int sh = 0; sh < 2; ++sh) {
-    for (int r = 0; r < m;) {
-      int e = r;
-      while (e < m && e - r < kShapeRows[sh] && rowPtr[e + 1] - rowPtr[r] <= kShapeNnz[sh]) ++e;
-      if (e == r) e = r + 1;
-      blk[sh].push_back(make_int4(r, e, rowPtr[r], rowPtr[e]));
-      r = e;
+  if (upload_csr(m, rowPtr, colInd, val, &op->A)) return 1;
+  if (const char* e = getenv("PREALPS_SPMM_LEAN")) op->lean = std::max(0, atoi(e));
+  if (getenv("PREALPS_SPMM_OVERLAP") != nullptr && nhalo > 0) {
+    // split: Aloc keeps the entries with column < m of every row; (brow, hptr, hcol, hval) the others
+    std::vector<int> lrp(m + 1, 0), lci, brow, hptr(1, 0), hcol;
+    std::vector<double> lv, hv;
+    lci.reserve(op->nnz); lv.reserve(op->nnz);
+    for (int r = 0; r < m; ++r) {
+      bool boundary = false;
+      for (int p = rowPtr[r]; p < rowPtr[r + 1]; ++p) {
+        if (colInd[p] < m) { lci.push_back(colInd[p]); lv.push_back(val[p]); }
+        else { hcol.push_back(colInd[p] - m); hv.push_back(val[p]); boundary = true; }
+      }
+      lrp[r + 1] = (int)lci.size();
+      if (boundary) { brow.push_back(r); hptr.push_back((int)hcol.size()); }
     }
-    op->nblk[sh] = (int)blk[sh].size();
+    if (lci.empty()) { lci.push_back(0); lv.push_back(0.0); }
+    if (upload_csr(m, lrp.data(), lci.data(), lv.data(), &op->Aloc)) return 1;
+    op->nbrow = (int)brow.size();
+    PCU_CUDA(cudaMalloc(&op->d_brow, sizeof(int) * std::max<size_t>(brow.size(), 1)));
+    PCU_CUDA(cudaMalloc(&op->d_hptr, sizeof(int) * hptr.size()));
+    PCU_CUDA(cudaMalloc(&op->d_hcol, sizeof(int) * std::max<size_t>(hcol.size(), 1)));
+    PCU_CUDA(cudaMalloc(&op->d_hval, sizeof(double) * std::max<size_t>(hv.size(), 1)));
+    PCU_CUDA(cudaMemcpy(op->d_brow, brow.data(), sizeof(int) * brow.size(), cudaMemcpyHostToDevice));
+    PCU_CUDA(cudaMemcpy(op->d_hptr, hptr.data(), sizeof(int) * hptr.size(), cudaMemcpyHostToDevice));
+    PCU_CUDA(cudaMemcpy(op->d_hcol, hcol.data(), sizeof(int) * hcol.size(), cudaMemcpyHostToDevice));
+    PCU_CUDA(cudaMemcpy(op->d_hval, hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice));
+    PCU_CUDA(cudaStreamCreateWithFlags(&op->comm_stream, cudaStreamNonBlocking));
+    PCU_CUDA(cudaEventCreateWithFlags(&op->ev_x, cudaEventDisableTiming));
+    PCU_CUDA(cudaEventCreateWithFlags(&op->ev_h, cudaEventDisableTiming));
+    op->overlap = true;
   }
-  if (const char* e = getenv("PREALPS_SPMM_LEAN")) {
-    op->lean = std::max(0, atoi(e));
-    for (const int4& b : blk[0])
-      if (b.w - b.z > kShapeNnz[0]) op->lean = 0;
-  }
-  PCU_CUDA(cudaMalloc(&op->d_rowPtr, sizeof(int) * (size_t)(m + 1)));
-  PCU_CUDA(cudaMalloc(&op->d_colInd, sizeof(int) * (size_t)std::max<int64_t>(op->nnz, 1)));
-  PCU_CUDA(cudaMalloc(&op->d_val, sizeof(double) * (size_t)std::max<int64_t>(op->nnz, 1)));
-  for (int sh = 0; sh < 2; ++sh) PCU_CUDA(cudaMalloc(&op->d_blk[sh], sizeof(int4) * std::max<size_t>(blk[sh].size(), 1)));
-  PCU_CUDA(cudaMemcpy(op->d_rowPtr, rowPtr, sizeof(int) * (size_t)(m + 1), cudaMemcpyHostToDevice));
-  PCU_CUDA(cudaMemcpy(op->d_colInd, colInd, sizeof(int) * (size_t)op->nnz, cudaMemcpyHostToDevice));
-  PCU_CUDA(cudaMemcpy(op->d_val, val, sizeof(double) * (size_t)op->nnz, cudaMemcpyHostToDevice));
-  for (int sh = 0; sh < 2; ++sh)
-    if (!blk[sh].empty())
-      PCU_CUDA(cudaMemcpy(op->d_blk[sh], blk[sh].data(), sizeof(int4) * blk[sh].size(), cudaMemcpyHostToDevice));
   *out = op;
   return 0;
 }
@@ -397,7 +479,14 @@ int pcu_spmm_destroy(pcu_spmm* op) {
   if (!op) return 0;
   cudaSetDevice(op->ctx->device);
   cudaStreamSynchronize(op->ctx->stream);
-  cudaFree(op->d_rowPtr); cudaFree(op->d_colInd); cudaFree(op->d_val); cudaFree(op->d_blk[0]); cudaFree(op->d_blk[1]);
+  free_csr(&op->A);
+  if (op->overlap) {
+    cudaStreamSynchronize(op->comm_stream);
+    free_csr(&op->Aloc);
+    cudaFree(op->d_brow); cudaFree(op->d_hptr); cudaFree(op->d_hcol); cudaFree(op->d_hval);
+    cudaEventDestroy(op->ev_x); cudaEventDestroy(op->ev_h);
+    cudaStreamDestroy(op->comm_stream);
+  }
   if (op->d_send_idx) cudaFree(op->d_send_idx);
   if (op->d_sendbuf) cudaFree(op->d_sendbuf);
   if (op->d_halo) cudaFree(op->d_halo);
@@ -429,52 +518,59 @@ double* pcu_spmm_halo_buffer(pcu_spmm* op, int t) {
   return op->d_halo;
 }
 
-int pcu_spmm_halo_pack(pcu_spmm* op, const double* X, int ldx, int t, double** packed_dev, int* nrows) {
-  if (ensure_halo_buffers(op, t)) return 1;
+static int halo_pack_on(pcu_spmm* op, const double* X, int ldx, int t, cudaStream_t st) {
   pcu_ctx* c = op->ctx;
   if (op->nsend > 0) {
     const int grid = stream_grid(c, (int64_t)op->nsend * t, 256, 4);
-    halo_pack_kernel<<<grid, 256, 0, c->stream>>>(X, ldx, t, op->d_send_idx, op->nsend, op->d_sendbuf);
+    halo_pack_kernel<<<grid, 256, 0, st>>>(X, ldx, t, op->d_send_idx, op->nsend, op->d_sendbuf);
     PCU_LAUNCH_CHECK(c);
   }
+  return 0;
+}
+
+int pcu_spmm_halo_pack(pcu_spmm* op, const double* X, int ldx, int t, double** packed_dev, int* nrows) {
+  if (ensure_halo_buffers(op, t)) return 1;
+  if (halo_pack_on(op, X, ldx, t, op->ctx->stream)) return 1;
   if (packed_dev) *packed_dev = op->d_sendbuf;
   if (nrows) *nrows = op->nsend;
   return 0;
 }
 
-int pcu_spmm_halo_exchange(pcu_spmm* op, const double* X, int ldx, int t) {
+// pack + grouped ncclSend/ncclRecv of the boundary rows on stream st
+static int halo_exchange_on(pcu_spmm* op, const double* X, int ldx, int t, cudaStream_t st) {
   pcu_ctx* c = op->ctx;
-  if (op->nnbr == 0) return 0;
   PCU_CHECK(c->nccl_comm != nullptr, "pcu_spmm_halo_exchange: %d neighbours but no NCCL communicator", op->nnbr);
-  if (pcu_spmm_halo_pack(op, X, ldx, t, nullptr, nullptr)) return 1;
+  if (halo_pack_on(op, X, ldx, t, st)) return 1;
   if (nccl_group_start(c)) return 1;
   for (int q = 0; q < op->nnbr; ++q) {
     const int ns = op->send_ptr[q + 1] - op->send_ptr[q], nr = op->recv_ptr[q + 1] - op->recv_ptr[q];
-    if (ns > 0 && nccl_send(c, op->d_sendbuf + (size_t)op->send_ptr[q] * t, (size_t)ns * t, 1, op->nbr_rank[q])) return 1;
-    if (nr > 0 && nccl_recv(c, op->d_halo + (size_t)op->recv_ptr[q] * t, (size_t)nr * t, 1, op->nbr_rank[q])) return 1;
+    if (ns > 0 && nccl_send(c, op->d_sendbuf + (size_t)op->send_ptr[q] * t, (size_t)ns * t, 1, op->nbr_rank[q], st)) return 1;
+    if (nr > 0 && nccl_recv(c, op->d_halo + (size_t)op->recv_ptr[q] * t, (size_t)nr * t, 1, op->nbr_rank[q], st)) return 1;
   }
   if (nccl_group_end(c)) return 1;
   return 0;
 }
 
-int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, int t) {
-  PCU_CHECK(op && X && Y && t >= 1, "pcu_spmm_apply: bad arguments");
-  PCU_CHECK(X != Y, "pcu_spmm_apply: X and Y must not alias");
+int pcu_spmm_halo_exchange(pcu_spmm* op, const double* X, int ldx, int t) {
+  if (op->nnbr == 0) return 0;
+  if (ensure_halo_buffers(op, t)) return 1;
+  return halo_exchange_on(op, X, ldx, t, op->ctx->stream);
+}
+
+// Y = A [X ; H] for one CSR of the operator (the whole panel, or its local part with H unused)
+static int launch_spmm(pcu_spmm* op, const CsrDev& A, const double* X, int ldx, double* Y, int ldy, int t) {
   pcu_ctx* c = op->ctx;
-  if (op->m == 0) return 0;
-  if (op->nhalo > 0 && ensure_halo_buffers(op, t)) return 1;
-  PCU_CHECK(t <= 32, "pcu_spmm_apply: t=%d > 32 is not supported", t);
   const int sh = (t <= 4) ? 1 : 0;
-  const int nblk = op->nblk[sh];
-  SpmmArgs a{op->d_rowPtr, op->d_colInd, op->d_val, op->d_blk[sh], op->m, X, ldx, op->d_halo, Y, ldy, t};
+  const int nblk = A.nblk[sh];
+  SpmmArgs a{A.rowPtr, A.colInd, A.val, A.blk[sh], op->m, X, ldx, op->d_halo, Y, ldy, t};
   const bool aligned = (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0);
   const bool pow2 = (t == 2 || t == 4 || t == 8 || t == 16 || t == 32);
   // 256-bit accesses need 32-byte aligned rows (the halo buffer has ld = t). They pay for short rows, where the
   // per-row instructions dominate and twice the rows per warp halves them (7-point: 126 -> 112 us at t = 8); with 27
   // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
   const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
-                    ((uintptr_t)op->d_halo % 32 == 0) && op->nnz <= 12 * (int64_t)op->m;
-  const bool lean = op->lean > 0 && aligned && pow2 && t >= 8 && ldx == t;
+                    ((uintptr_t)op->d_halo % 32 == 0) && A.nnz <= 12 * (int64_t)op->m;
+  const bool lean = op->lean > 0 && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
   if (lean) {
     if (t == 8) launch_lean<8>(a, nblk, wide, op->lean, c->stream);
     else if (t == 16) launch_lean<16>(a, nblk, wide, op->lean, c->stream);
@@ -501,6 +597,47 @@ int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, i
     spmm_kernel_generic<<<nblk, kThreads, 0, c->stream>>>(a);
   }
   PCU_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, int t) {
+  PCU_CHECK(op && X && Y && t >= 1, "pcu_spmm_apply: bad arguments");
+  PCU_CHECK(X != Y, "pcu_spmm_apply: X and Y must not alias");
+  if (op->m == 0) return 0;
+  if (op->nhalo > 0 && ensure_halo_buffers(op, t)) return 1;
+  PCU_CHECK(t <= 32, "pcu_spmm_apply: t=%d > 32 is not supported", t);
+  return launch_spmm(op, op->A, X, ldx, Y, ldy, t);
+}
+
+// halo exchange over NCCL + product.  Default: one after the other on the library stream.  PREALPS_SPMM_OVERLAP=1 (opt-in,
+// written after the last GPU session of round 1, not measured yet): the exchange runs on a second stream while the local
+// part of the product (entries with column < m: > 99 % of them) runs on the library stream, then halo_add_kernel adds
+// the halo entries of the boundary rows -- what the reference does with MPI_Isend / diagonal block / MPI_Irecv
+// (ref: utils/cplm_v0/cplm_v0_matmult_v2.c:182-276).
+int pcu_spmm_apply_exchange(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, int t) {
+  PCU_CHECK(op && X && Y && t >= 1 && t <= 32, "pcu_spmm_apply_exchange: bad arguments");
+  PCU_CHECK(X != Y, "pcu_spmm_apply_exchange: X and Y must not alias");
+  pcu_ctx* c = op->ctx;
+  if ((op->nhalo > 0 || op->nsend > 0) && ensure_halo_buffers(op, t)) return 1;
+  if (!op->overlap || op->nnbr == 0) {
+    if (op->nnbr > 0 && halo_exchange_on(op, X, ldx, t, c->stream)) return 1;
+    if (op->m == 0) return 0;
+    return launch_spmm(op, op->A, X, ldx, Y, ldy, t);
+  }
+  // X is ready once everything queued on the library stream so far has run (that also orders this exchange after
+  // the previous product's reads of the halo buffer)
+  PCU_CUDA(cudaEventRecord(op->ev_x, c->stream));
+  PCU_CUDA(cudaStreamWaitEvent(op->comm_stream, op->ev_x, 0));
+  if (halo_exchange_on(op, X, ldx, t, op->comm_stream)) return 1;
+  PCU_CUDA(cudaEventRecord(op->ev_h, op->comm_stream));
+  if (op->m > 0 && launch_spmm(op, op->Aloc, X, ldx, Y, ldy, t)) return 1;
+  PCU_CUDA(cudaStreamWaitEvent(c->stream, op->ev_h, 0));
+  if (op->nbrow > 0) {
+    const int grid = stream_grid(c, (int64_t)op->nbrow * 16, kThreads, 8);
+    halo_add_kernel<<<grid, kThreads, 0, c->stream>>>(op->nbrow, op->d_brow, op->d_hptr, op->d_hcol, op->d_hval, op->d_halo, t, Y,
+                                                      ldy);
+    PCU_LAUNCH_CHECK(c);
+  }
   return 0;
 }
 

@@ -68,3 +68,24 @@ def test_nccl_solve_matches_reference(world, case, tmp_path):
         assert r["hist_dev"] < 1e-6
         assert r["sol_dev"] < 1e-7
         assert r["nhalo"] > 0 and len(r["dep"]) > 0
+
+
+@pytest.mark.skipif(not os.environ.get("PREALPS_TEST_CANDIDATES"),
+                    reason="opt-in kernels that have not been measured on a B200 yet (PREALPS_TEST_CANDIDATES=1)")
+@pytest.mark.parametrize("world", [2, 8])
+def test_nccl_solve_with_overlapped_halo_exchange(world, tmp_path):
+    """PREALPS_SPMM_OVERLAP=1: halo exchange on a second stream next to the local part of the product, halo entries of
+    the boundary rows added afterwards (same summation order): same iterations and history as the reference"""
+    if capi.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    script = tmp_path / "run.py"
+    script.write_text(SCRIPT % {"root": ROOT, "case": "poisson7_n12_s8_t8_odir", "out": str(tmp_path)})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(29560 + world), str(script)],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, PREALPS_SPMM_OVERLAP="1"))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    res = [json.load(open(str(tmp_path / ("result_%d.json" % r)))) for r in range(world)]
+    for r in res:
+        assert abs(r["iter"] - r["ref_iter"]) <= 1
+        assert r["hist_dev"] < 1e-6
+        assert r["sol_dev"] < 1e-7

@@ -27,3 +27,7 @@ done
 python bench.py --no-cpu-baseline > $out/cand_bench_default.json 2> $out/cand_bench_default.err
 PREALPS_SPMM_LEAN=1 PREALPS_BJ_ASM_PREFETCH=1 PREALPS_BJ_GRAPH=1 python bench.py --no-cpu-baseline > $out/cand_bench_all.json 2> $out/cand_bench_all.err
 grep -h '"t": 8,' $out/cand_spmm_*.jsonl; tail -n 3 $out/cand_tests.log; cat $out/cand_bj.log | grep -v METIS | tail -n 20
+# multi-GPU candidates need `gpurun --gpus 2` (or 8):
+#   PREALPS_TEST_CANDIDATES=1 python -m pytest tests/test_gpu_multi.py -q -m gpu -k overlapped
+#   for v in "" PREALPS_SPMM_OVERLAP=1 PREALPS_BJ_GRAPH=1 "PREALPS_SPMM_OVERLAP=1 PREALPS_BJ_GRAPH=1 PREALPS_BJ_ASM_PREFETCH=1"; do
+#     env $v python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8; done
