@@ -572,9 +572,13 @@ static int launch_spmm(pcu_spmm* op, const CsrDev& A, const double* X, int ldx, 
                     ((uintptr_t)op->d_halo % 32 == 0) && A.nnz <= 12 * (int64_t)op->m;
   const bool lean = op->lean > 0 && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
   if (lean) {
-    if (t == 8) launch_lean<8>(a, nblk, wide, op->lean, c->stream);
-    else if (t == 16) launch_lean<16>(a, nblk, wide, op->lean, c->stream);
-    else launch_lean<32>(a, nblk, wide, op->lean, c->stream);
+    // the lean kernel also takes the 4-columns-per-lane mapping for long rows when a row block still has a row for every
+    // lane group (27-point stencil: 56 rows per block, 32 groups at t = 32)
+    const bool align32 = (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) && ((uintptr_t)op->d_halo % 32 == 0);
+    const bool wide_lean = wide || (align32 && (int64_t)(kThreads / (t / 4)) * nblk <= (int64_t)op->m);
+    if (t == 8) launch_lean<8>(a, nblk, wide_lean, op->lean, c->stream);
+    else if (t == 16) launch_lean<16>(a, nblk, wide_lean, op->lean, c->stream);
+    else launch_lean<32>(a, nblk, wide_lean, op->lean, c->stream);
   } else if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {
