@@ -17,223 +17,9 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include "spmm_kernels.cuh"
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kNnzCap = 1792;   // staged entries per CTA (21 KB of shared memory) and rows per CTA: the static arrays
-constexpr int kRowCap = 256;    // are sized for the larger of the two row-block shapes below
-// Row blocks come in two shapes. With few lanes per row (t <= 4) a CTA covers many rows per pass and larger blocks
-// amortise the descriptor + staging latency (7-point, t = 1: 78 -> 61 us); from t = 8 up the smaller blocks win
-// (t = 32: 289 vs 316 us): more CTAs in different phases per SM.
-constexpr int kShapeRows[2] = {128, 256};
-constexpr int kShapeNnz[2] = {1536, 1792};
-
-struct SpmmArgs {
-  const int* rowPtr;
-  const int* colInd;
-  const double* val;
-  const int4* blk;  // per row block: {first row, end row, first entry, end entry} -- one load instead of a chain of three
-  int m;
-  const double* X;
-  int ldx;
-  const double* H;  // halo rows, ld = t
-  double* Y;
-  int ldy;
-  int t;
-};
-
-__device__ __forceinline__ double2 ldg2(const double* p) {
-  return __ldg(reinterpret_cast<const double2*>(p));
-}
-
-// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): 4 columns of a row per lane
-__device__ __forceinline__ void ldg4(const double* p, double (&x)[4]) {
-  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
-}
-__device__ __forceinline__ void stg4(double* p, const double (&x)[4]) {
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
-}
-
-// T columns, G = T / CPL lanes per row, each lane owns CPL adjacent columns: 4 with 256-bit accesses (T >= 8, rows
-// 32-byte aligned: half the lanes, so twice the rows per warp and half the instructions per row), else 2, or 1 (T == 1).
-template <int T, int CPL>
-__global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
-  constexpr int G = T / CPL;
-  constexpr int NG = kThreads / G;
-  __shared__ int s_col[kNnzCap];
-  __shared__ double s_val[kNnzCap];
-  __shared__ int s_rp[kRowCap + 1];
-
-  const int4 d = __ldg(a.blk + blockIdx.x);
-  const int r0 = d.x, r1 = d.y, p0 = d.z, p1 = d.w;
-  const int n = p1 - p0;
-  const int tid = threadIdx.x;
-
-  if (n <= kNnzCap) {
-    for (int i = tid; i < n; i += kThreads) {
-      s_col[i] = __ldg(a.colInd + p0 + i);
-      s_val[i] = __ldg(a.val + p0 + i);
-    }
-    for (int i = tid; i <= r1 - r0; i += kThreads) s_rp[i] = __ldg(a.rowPtr + r0 + i) - p0;
-    __syncthreads();
-    const int grp = tid / G, lig = tid % G;
-    for (int r = r0 + grp; r < r1; r += NG) {
-      const int b = s_rp[r - r0], e = s_rp[r - r0 + 1];
-      if (CPL == 4) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-        for (int p = b; p < e; ++p) {
-          const int c = s_col[p];
-          const double v = s_val[p];
-          const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * a.t;
-          double x[4];
-          ldg4(src + 4 * lig, x);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = fma(v, x[j], acc[j]);
-        }
-        stg4(a.Y + (size_t)r * a.ldy + 4 * lig, acc);
-        continue;
-      }
-      double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 4
-      for (int p = b; p < e; ++p) {
-        const int c = s_col[p];
-        const double v = s_val[p];
-        const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * a.t;
-        if (CPL == 2) {
-          const double2 x = ldg2(src + 2 * lig);
-          acc0 = fma(v, x.x, acc0);
-          acc1 = fma(v, x.y, acc1);
-        } else {
-          acc0 = fma(v, __ldg(src), acc0);
-        }
-      }
-      double* dst = a.Y + (size_t)r * a.ldy;
-      if (CPL == 2) *reinterpret_cast<double2*>(dst + 2 * lig) = make_double2(acc0, acc1);
-      else dst[0] = acc0;
-    }
-  } else {
-    // a single very long row (the host never puts two rows in an oversized block):
-    // all threads stride over it, then a fixed-order tree reduction in shared memory.
-    double* red = s_val;  // kNnzCap >= kThreads * 2
-    const int r = r0;
-    for (int c0 = 0; c0 < T; c0 += 2) {
-      double acc0 = 0.0, acc1 = 0.0;
-      for (int p = p0 + tid; p < p1; p += kThreads) {
-        const int c = a.colInd[p];
-        const double v = a.val[p];
-        const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * a.t;
-        acc0 = fma(v, src[c0], acc0);
-        if (c0 + 1 < T) acc1 = fma(v, src[c0 + 1], acc1);
-      }
-      red[tid] = acc0;
-      red[kThreads + tid] = acc1;
-      __syncthreads();
-      for (int s = kThreads / 2; s > 0; s >>= 1) {
-        if (tid < s) { red[tid] += red[tid + s]; red[kThreads + tid] += red[kThreads + tid + s]; }
-        __syncthreads();
-      }
-      if (tid == 0) {
-        a.Y[(size_t)r * a.ldy + c0] = red[0];
-        if (c0 + 1 < T) a.Y[(size_t)r * a.ldy + c0 + 1] = red[kThreads];
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// Candidate kernel, opt-in with PREALPS_SPMM_LEAN=1 (written after the last GPU session of round 1: compiled and its
-// SASS read, NOT yet run on a B200 -- measure before making it the default).  Same mapping, same summation order
-// and therefore the same bits as spmm_kernel<T, CPL>; what changes is the work per entry in the row phase.  The
-// SASS of spmm_kernel<8, 4> spends ~22 instructions per entry and lane: LDS col, LDS val, a compare, 4-5 predicated
-// LDC of the kernel arguments, two predicated IMAD.WIDE, four predicated LEA, a 64-bit add, LDG.256 and 4 DFMA.
-// Here the thread that stages an entry (once per entry, 32 entries per warp instruction) resolves "block row or
-// halo row" and the row stride into ONE 64-bit byte offset relative to X, stored next to the value, so the row phase
-// is LDS.128 + 64-bit add + LDG + CPL DFMA per entry.  Needs ldx == T (rows of X and of the halo buffer are both
-// T doubles apart) and every row block of shape 0 within the staging capacity.
-// NB > 1 (PREALPS_SPMM_LEAN=2 or 4): the gathers of NB consecutive entries of a row are issued back to back before
-// their FMAs (which keep their order).  ptxas only schedules them that way when __launch_bounds__ names a minimum
-// number of CTAs per SM (MINB): with the bare (256) bound it aims at 32 registers / full occupancy and sinks every load
-// next to its consumer -- one gather in flight per lane, which is also what spmm_kernel does.  NB = 2: <= 48 registers,
-// 5 CTAs/SM; NB = 4: <= 64 registers, 4 CTAs/SM.
-template <int T, int CPL, int NB, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) spmm_lean_kernel(SpmmArgs a) {
-  static_assert(CPL == 2 || CPL == 4, "lanes own 2 or 4 adjacent columns");
-  constexpr int G = T / CPL;
-  constexpr int NG = kThreads / G;
-  constexpr int kCap = kShapeNnz[0];
-  __shared__ double2 s_ent[kCap];  // {value, bit pattern of the source row's byte offset from X}
-  __shared__ int s_rp[kShapeRows[0] + 1];
-
-  const int4 d = __ldg(a.blk + blockIdx.x);
-  const int r0 = d.x, r1 = d.y, p0 = d.z, p1 = d.w;
-  const int n = p1 - p0;  // <= kCap: checked on the host before this kernel is chosen
-  const int tid = threadIdx.x;
-  // halo row c - m lives at H + (c - m) * T doubles = X + hdelta + c * T * 8 bytes (unused without a halo: c < m)
-  const long long hdelta = (long long)(reinterpret_cast<intptr_t>(a.H) - reinterpret_cast<intptr_t>(a.X)) -
-                           (long long)a.m * (T * 8);
-  for (int i = tid; i < n; i += kThreads) {
-    const int c = __ldg(a.colInd + p0 + i);
-    const long long off = (long long)c * (T * 8) + (c < a.m ? 0ll : hdelta);
-    s_ent[i] = make_double2(__ldg(a.val + p0 + i), __longlong_as_double(off));
-  }
-  for (int i = tid; i <= r1 - r0; i += kThreads) s_rp[i] = __ldg(a.rowPtr + r0 + i) - p0;
-  __syncthreads();
-  const int grp = tid / G, lig = tid % G;
-  const char* xl = reinterpret_cast<const char*>(a.X + CPL * lig);
-  for (int r = r0 + grp; r < r1; r += NG) {
-    const int b = s_rp[r - r0], e = s_rp[r - r0 + 1];
-    double acc[CPL];
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) acc[j] = 0.0;
-    int p = b;
-    if constexpr (NB > 1) {
-      for (; p + NB <= e; p += NB) {
-        double2 en[NB];
-        double x[NB][4];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) en[k] = s_ent[p + k];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          const double* src = reinterpret_cast<const double*>(xl + __double_as_longlong(en[k].y));
-          if constexpr (CPL == 4) {
-            ldg4(src, x[k]);
-          } else {
-            const double2 v = ldg2(src);
-            x[k][0] = v.x;
-            x[k][1] = v.y;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < NB; ++k)
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) acc[j] = fma(en[k].x, x[k][j], acc[j]);
-      }
-    }
-#pragma unroll 4
-    for (; p < e; ++p) {
-      const double2 en = s_ent[p];
-      const double* src = reinterpret_cast<const double*>(xl + __double_as_longlong(en.y));
-      if constexpr (CPL == 4) {
-        double x[4];
-        ldg4(src, x);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fma(en.x, x[j], acc[j]);
-      } else {
-        const double2 x = ldg2(src);
-        acc[0] = fma(en.x, x.x, acc[0]);
-        acc[1] = fma(en.x, x.y, acc[1]);
-      }
-    }
-    double* dst = a.Y + (size_t)r * a.ldy + CPL * lig;
-    if constexpr (CPL == 4) {
-      stg4(dst, acc);
-    } else {
-      *reinterpret_cast<double2*>(dst) = make_double2(acc[0], acc[1]);
-    }
-  }
-}
 
 template <int T, int CPL>
 void launch_lean_nb(const SpmmArgs& a, int nblk, int nb, cudaStream_t st) {
@@ -246,92 +32,6 @@ template <int T>
 void launch_lean(const SpmmArgs& a, int nblk, bool wide, int nb, cudaStream_t st) {
   if (wide) launch_lean_nb<T, 4>(a, nblk, nb, st);
   else launch_lean_nb<T, 2>(a, nblk, nb, st);
-}
-
-// any 1 <= t <= 32: 16 lanes per row, lane owns columns lig and lig+16
-__global__ void __launch_bounds__(kThreads) spmm_kernel_generic(SpmmArgs a) {
-  constexpr int G = 16, NG = kThreads / G;
-  __shared__ int s_col[kNnzCap];
-  __shared__ double s_val[kNnzCap];
-  const int4 d = __ldg(a.blk + blockIdx.x);
-  const int r0 = d.x, r1 = d.y;
-  const int tid = threadIdx.x, grp = tid / G, lig = tid % G;
-  const int t = a.t;
-  // rows are processed in sub-blocks that fit the staging buffers
-  for (int rs = r0; rs < r1;) {
-    int re = rs;
-    const int p0 = a.rowPtr[rs];
-    while (re < r1 && a.rowPtr[re + 1] - p0 <= kNnzCap) ++re;
-    if (re == rs) {  // one row longer than the buffer: direct global reads
-      const int p1 = a.rowPtr[rs + 1];
-      if (grp == 0) {
-        double acc0 = 0.0, acc1 = 0.0;
-        for (int p = p0; p < p1; ++p) {
-          const int c = a.colInd[p];
-          const double v = a.val[p];
-          const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * t;
-          if (lig < t) acc0 = fma(v, src[lig], acc0);
-          if (lig + 16 < t) acc1 = fma(v, src[lig + 16], acc1);
-        }
-        if (lig < t) a.Y[(size_t)rs * a.ldy + lig] = acc0;
-        if (lig + 16 < t) a.Y[(size_t)rs * a.ldy + lig + 16] = acc1;
-      }
-      rs += 1;
-      continue;
-    }
-    const int n = a.rowPtr[re] - p0;
-    __syncthreads();
-    for (int i = tid; i < n; i += kThreads) { s_col[i] = a.colInd[p0 + i]; s_val[i] = a.val[p0 + i]; }
-    __syncthreads();
-    for (int r = rs + grp; r < re; r += NG) {
-      const int b = a.rowPtr[r] - p0, e = a.rowPtr[r + 1] - p0;
-      double acc0 = 0.0, acc1 = 0.0;
-      for (int p = b; p < e; ++p) {
-        const int c = s_col[p];
-        const double v = s_val[p];
-        const double* src = (c < a.m) ? a.X + (size_t)c * a.ldx : a.H + (size_t)(c - a.m) * t;
-        if (lig < t) acc0 = fma(v, __ldg(src + lig), acc0);
-        if (lig + 16 < t) acc1 = fma(v, __ldg(src + lig + 16), acc1);
-      }
-      if (lig < t) a.Y[(size_t)r * a.ldy + lig] = acc0;
-      if (lig + 16 < t) a.Y[(size_t)r * a.ldy + lig + 16] = acc1;
-    }
-    rs = re;
-  }
-}
-
-__global__ void halo_pack_kernel(const double* __restrict__ X, int ldx, int t, const int* __restrict__ idx,
-                                 int nrows, double* __restrict__ out) {
-  const int64_t total = (int64_t)nrows * t;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / t), c = (int)(i % t);
-    out[i] = X[(size_t)idx[r] * ldx + c];
-  }
-}
-
-// Overlapped product (opt-in, PREALPS_SPMM_OVERLAP=1): Y[r, :] += sum_k hval[k] * H[hcol[k], :] for the rows that read
-// halo rows, after the local kernel has written the partial sums of the entries with column < m.  Halo columns sort
-// after the local ones, so continuing each row's FMA chain from the stored partial sum reproduces the merged kernel's
-// summation order bit for bit.  16 lanes per row, lane owns columns lig and lig + 16 (any t <= 32).
-__global__ void __launch_bounds__(kThreads) halo_add_kernel(int nb, const int* __restrict__ brow, const int* __restrict__ hptr,
-                                                            const int* __restrict__ hcol, const double* __restrict__ hval,
-                                                            const double* __restrict__ H, int t, double* Y, int ldy) {
-  constexpr int G = 16;
-  const int gid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / G), lig = threadIdx.x % G;
-  const int ngroups = (int)((long long)gridDim.x * blockDim.x / G);
-  for (int q = gid; q < nb; q += ngroups) {
-    double* y = Y + (size_t)brow[q] * ldy;
-    const int b = hptr[q], e = hptr[q + 1];
-    double acc0 = (lig < t) ? y[lig] : 0.0, acc1 = (lig + 16 < t) ? y[lig + 16] : 0.0;
-    for (int p = b; p < e; ++p) {
-      const double v = hval[p];
-      const double* src = H + (size_t)hcol[p] * t;
-      if (lig < t) acc0 = fma(v, __ldg(src + lig), acc0);
-      if (lig + 16 < t) acc1 = fma(v, __ldg(src + lig + 16), acc1);
-    }
-    if (lig < t) y[lig] = acc0;
-    if (lig + 16 < t) y[lig + 16] = acc1;
-  }
 }
 
 // one CSR on the device with its row blocks
@@ -347,16 +47,9 @@ struct CsrDev {
 
 int upload_csr(int m, const int* rowPtr, const int* colInd, const double* val, CsrDev* d) {
   d->nnz = rowPtr[m];
-  // row blocks: <= kRowCap rows and <= kNnzCap entries; an over-long row gets a block of its own
   std::vector<int4> blk[2];
   for (int sh = 0; sh < 2; ++sh) {
-    for (int r = 0; r < m;) {
-      int e = r;
-      while (e < m && e - r < kShapeRows[sh] && rowPtr[e + 1] - rowPtr[r] <= kShapeNnz[sh]) ++e;
-      if (e == r) e = r + 1;
-      blk[sh].push_back(make_int4(r, e, rowPtr[r], rowPtr[e]));
-      r = e;
-    }
+    build_row_blocks(m, rowPtr, sh, &blk[sh]);
     d->nblk[sh] = (int)blk[sh].size();
   }
   for (const int4& b : blk[0])
@@ -443,18 +136,9 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
   if (const char* e = getenv("PREALPS_SPMM_LEAN")) op->lean = std::max(0, atoi(e));
   if (getenv("PREALPS_SPMM_OVERLAP") != nullptr && nhalo > 0) {
     // split: Aloc keeps the entries with column < m of every row; (brow, hptr, hcol, hval) the others
-    std::vector<int> lrp(m + 1, 0), lci, brow, hptr(1, 0), hcol;
+    std::vector<int> lrp, lci, brow, hptr, hcol;
     std::vector<double> lv, hv;
-    lci.reserve(op->nnz); lv.reserve(op->nnz);
-    for (int r = 0; r < m; ++r) {
-      bool boundary = false;
-      for (int p = rowPtr[r]; p < rowPtr[r + 1]; ++p) {
-        if (colInd[p] < m) { lci.push_back(colInd[p]); lv.push_back(val[p]); }
-        else { hcol.push_back(colInd[p] - m); hv.push_back(val[p]); boundary = true; }
-      }
-      lrp[r + 1] = (int)lci.size();
-      if (boundary) { brow.push_back(r); hptr.push_back((int)hcol.size()); }
-    }
+    split_local_halo(m, rowPtr, colInd, val, &lrp, &lci, &lv, &brow, &hptr, &hcol, &hv);
     if (lci.empty()) { lci.push_back(0); lv.push_back(0.0); }
     if (upload_csr(m, lrp.data(), lci.data(), lv.data(), &op->Aloc)) return 1;
     op->nbrow = (int)brow.size();
