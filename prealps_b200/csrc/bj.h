@@ -104,6 +104,7 @@ struct pcu_bj {
   // opt-in (PREALPS_BJ_GRAPH=1): the launch chain of one apply, captured once per argument tuple and replayed
   struct ApplyGraph {
     const double* B; int ldb; double* X; int ldx; int t;
+    int flags;              // environment switches baked into the captured launches (bit 0: PREALPS_BJ_ASM_PREFETCH)
     cudaGraphExec_t exec;   // nullptr: tuple seen once, captured on its next use
     long long kernels;      // launches the chain contains (added to the context's launch counter on every replay)
   };

@@ -642,8 +642,9 @@ constexpr size_t kMaxGraphs = 32;
 
 int apply_graphed(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   pcu_ctx* c = bj->ctx;
+  const int flags = getenv("PREALPS_BJ_ASM_PREFETCH") != nullptr ? 1 : 0;
   for (auto& g : bj->graphs) {
-    if (g.B != B || g.ldb != ldb || g.X != X || g.ldx != ldx || g.t != t) continue;
+    if (g.B != B || g.ldb != ldb || g.X != X || g.ldx != ldx || g.t != t || g.flags != flags) continue;
     if (g.exec) {
       PCU_CUDA(cudaGraphLaunch(g.exec, c->stream));
       c->launches += g.kernels;
@@ -671,7 +672,7 @@ int apply_graphed(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int 
   }
   const bool known = [&] {
     for (auto& g : bj->graphs)
-      if (g.B == B && g.ldb == ldb && g.X == X && g.ldx == ldx && g.t == t) return true;
+      if (g.B == B && g.ldb == ldb && g.X == X && g.ldx == ldx && g.t == t && g.flags == flags) return true;
     return false;
   }();
   if (known) {  // fell out of the loop: capture failed
@@ -679,7 +680,7 @@ int apply_graphed(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int 
     bj->graph_failed = true;
     set_error("pcu_bj_apply: CUDA graph capture of the apply chain failed, using plain launches");
   } else if (bj->graphs.size() < kMaxGraphs) {
-    bj->graphs.push_back(pcu_bj::ApplyGraph{B, ldb, X, ldx, t, nullptr, 0});
+    bj->graphs.push_back(pcu_bj::ApplyGraph{B, ldb, X, ldx, t, flags, nullptr, 0});
   }
   return dispatch_apply(bj, B, ldb, X, ldx, t);
 }

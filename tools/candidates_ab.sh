@@ -16,13 +16,8 @@ for nb in 1 2 4; do  # gathers in flight per lane
   PREALPS_SPMM_LEAN=$nb python tools/spmm_sweep.py 128 > $out/cand_spmm_lean$nb.jsonl 2> $out/cand_spmm_lean$nb.err
 done
 # block-Jacobi apply, 8 subdomains of 64^3 on this GPU (the N=1 bench) and ONE 64^3 subdomain (what each GPU holds at N=8)
-for sub in 8 1; do
-  n=128; [ $sub = 1 ] && n=64
-  for v in "" "PREALPS_BJ_ASM_PREFETCH=1" "PREALPS_BJ_GRAPH=1" "PREALPS_BJ_ASM_PREFETCH=1 PREALPS_BJ_GRAPH=1"; do
-    echo "== n=$n subdomains=$sub $v" >> $out/cand_bj.log
-    env SUBDOMAINS=$sub $v python tools/profile_apply.py $n 1 20 8 >> $out/cand_bj.log 2>&1
-  done
-done
+python tools/variants.py 128 8 8 > $out/cand_bj.log 2>&1
+python tools/variants.py 64 1 8 >> $out/cand_bj.log 2>&1
 # whole iterations with everything on
 python bench.py --no-cpu-baseline > $out/cand_bench_default.json 2> $out/cand_bench_default.err
 PREALPS_SPMM_LEAN=1 PREALPS_BJ_ASM_PREFETCH=1 PREALPS_BJ_GRAPH=1 python bench.py --no-cpu-baseline > $out/cand_bench_all.json 2> $out/cand_bench_all.err

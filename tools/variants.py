@@ -1,19 +1,24 @@
-"""tools/variants.py -- time the block-Jacobi apply on the bench operator (Poisson n^3, `nsub` subdomains on this GPU):
-    python tools/variants.py [n = 128] [0] [nsub = 8]"""
+"""tools/variants.py -- time the block-Jacobi apply on the bench operator (Poisson n^3, `nsub` subdomains on this GPU) under
+each environment switch of bj_solve.cu that is read per apply:
+    python tools/variants.py [n = 128] [nsub = 8] [t = 8]
+(nsub = 1 with n = 64 is what one GPU of an 8-GPU run of the 128^3 problem holds.)"""
 import ctypes as C
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from prealps_b200 import capi  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-variants = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3, 4]
-nsub = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+nsub = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+t = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+SWITCHES = [(), ("PREALPS_BJ_ASM_PREFETCH",), ("PREALPS_BJ_GRAPH",), ("PREALPS_BJ_ASM_PREFETCH", "PREALPS_BJ_GRAPH")]
 assert capi.lib.preAlps_b200_OperatorBuildStencil(0, n, nsub, 0, nsub) == 0
 assert capi.lib.preAlps_b200_BlockJacobiCreate() == 0
-for t in (8,):
-    for v in variants:
-        os.environ["PREALPS_BJ_VARIANT"] = str(v)
-        ms = C.c_float()
-        capi.lib.preAlps_b200_BenchKernel(1, t, 5, 1, C.byref(ms))
-        b = capi.stat("bj_bytes_t%d" % t)
-        print("variant %d t=%d: %.3f ms  %.1f GB/s" % (v, t, ms.value, b / ms.value / 1e6), flush=True)
+for on in SWITCHES:
+    for name in ("PREALPS_BJ_ASM_PREFETCH", "PREALPS_BJ_GRAPH"):
+        os.environ.pop(name, None)
+    for name in on:
+        os.environ[name] = "1"
+    ms = C.c_float()
+    capi.lib.preAlps_b200_BenchKernel(1, t, 20, 1, C.byref(ms))
+    b = capi.stat("bj_bytes_t%d" % t)
+    print("%-50s t=%d: %.3f ms  %.1f GB/s" % (" ".join(on) or "default", t, ms.value, b / ms.value / 1e6), flush=True)
