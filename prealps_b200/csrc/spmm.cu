@@ -29,6 +29,17 @@ void launch_lean_nb(const SpmmArgs& a, int nblk, int nb, cudaStream_t st) {
 }
 
 template <int T>
+void launch_bulk(const SpmmArgs& a, int nblk, bool wide, bool halo, cudaStream_t st) {
+  if (wide) {
+    if (halo) spmm_bulk_kernel<T, 4, true><<<nblk, kThreads, 0, st>>>(a);
+    else spmm_bulk_kernel<T, 4, false><<<nblk, kThreads, 0, st>>>(a);
+  } else {
+    if (halo) spmm_bulk_kernel<T, 2, true><<<nblk, kThreads, 0, st>>>(a);
+    else spmm_bulk_kernel<T, 2, false><<<nblk, kThreads, 0, st>>>(a);
+  }
+}
+
+template <int T>
 void launch_lean(const SpmmArgs& a, int nblk, bool wide, int nb, cudaStream_t st) {
   if (wide) launch_lean_nb<T, 4>(a, nblk, nb, st);
   else launch_lean_nb<T, 2>(a, nblk, nb, st);
@@ -55,8 +66,9 @@ int upload_csr(int m, const int* rowPtr, const int* colInd, const double* val, C
   for (const int4& b : blk[0])
     if (b.w - b.z > kShapeNnz[0]) d->fits0 = false;
   PCU_CUDA(cudaMalloc(&d->rowPtr, sizeof(int) * (size_t)(m + 1)));
-  PCU_CUDA(cudaMalloc(&d->colInd, sizeof(int) * (size_t)std::max<int64_t>(d->nnz, 1)));
-  PCU_CUDA(cudaMalloc(&d->val, sizeof(double) * (size_t)std::max<int64_t>(d->nnz, 1)));
+  // 16 bytes of slack: spmm_bulk_kernel rounds the size of its bulk copies up to a multiple of 16
+  PCU_CUDA(cudaMalloc(&d->colInd, sizeof(int) * (size_t)(d->nnz + 4)));
+  PCU_CUDA(cudaMalloc(&d->val, sizeof(double) * (size_t)(d->nnz + 2)));
   for (int sh = 0; sh < 2; ++sh) PCU_CUDA(cudaMalloc(&d->blk[sh], sizeof(int4) * std::max<size_t>(blk[sh].size(), 1)));
   PCU_CUDA(cudaMemcpy(d->rowPtr, rowPtr, sizeof(int) * (size_t)(m + 1), cudaMemcpyHostToDevice));
   PCU_CUDA(cudaMemcpy(d->colInd, colInd, sizeof(int) * (size_t)d->nnz, cudaMemcpyHostToDevice));
@@ -80,6 +92,7 @@ struct pcu_spmm {
   int64_t nnz = 0;
   CsrDev A;           // the local row panel, columns >= m read the halo buffer
   int lean = 0;       // PREALPS_SPMM_LEAN=1|2|4 (gathers in flight per lane): spmm_lean_kernel from t = 8 up
+  bool bulk = false;  // PREALPS_SPMM_BULK=1: spmm_bulk_kernel (cp.async.bulk staging) from t = 8 up
   // PREALPS_SPMM_OVERLAP=1 and nhalo > 0: the panel split into its entries with column < m (Aloc, same rows) and the halo
   // entries of the boundary rows; the halo exchange then runs on comm_stream next to the local kernel
   bool overlap = false;
@@ -134,6 +147,7 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
               colInd[p], (long long)p);
   if (upload_csr(m, rowPtr, colInd, val, &op->A)) return 1;
   if (const char* e = getenv("PREALPS_SPMM_LEAN")) op->lean = std::max(0, atoi(e));
+  if (const char* e = getenv("PREALPS_SPMM_BULK")) op->bulk = atoi(e) != 0;
   if (getenv("PREALPS_SPMM_OVERLAP") != nullptr && nhalo > 0) {
     // split: Aloc keeps the entries with column < m of every row; (brow, hptr, hcol, hval) the others
     std::vector<int> lrp, lci, brow, hptr, hcol;
@@ -255,7 +269,13 @@ static int launch_spmm(pcu_spmm* op, const CsrDev& A, const double* X, int ldx, 
   const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
                     ((uintptr_t)op->d_halo % 32 == 0) && A.nnz <= 12 * (int64_t)op->m;
   const bool lean = op->lean > 0 && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
-  if (lean) {
+  const bool bulk = op->bulk && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
+  if (bulk) {
+    const bool halo = (&A == &op->A) && op->nhalo > 0;  // the local part of the overlapped product has no column >= m
+    if (t == 8) launch_bulk<8>(a, nblk, wide, halo, c->stream);
+    else if (t == 16) launch_bulk<16>(a, nblk, wide, halo, c->stream);
+    else launch_bulk<32>(a, nblk, wide, halo, c->stream);
+  } else if (lean) {
     // the lean kernel also takes the 4-columns-per-lane mapping for long rows when a row block still has a row for every
     // lane group (27-point stencil: 56 rows per block, 32 groups at t = 32)
     const bool align32 = (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) && ((uintptr_t)op->d_halo % 32 == 0);

@@ -230,6 +230,118 @@ __global__ void __launch_bounds__(kThreads, MINB) spmm_lean_kernel(SpmmArgs a) {
   }
 }
 
+// ---- bulk-copy staging (opt-in, PREALPS_SPMM_BULK=1; written after the last GPU session of round 1, not measured yet)
+#ifndef PCU_EMUL
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// cp.async.bulk global -> shared (SASS UBLKCP): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+               "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned phase) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(phase)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void pcu_trap() { __trap(); }
+#else
+inline void mbar_init(unsigned long long*, unsigned) {}
+inline void fence_mbar_init() {}
+inline void mbar_arrive_expect_tx(unsigned long long*, unsigned) {}
+inline void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long*) {
+  pcu_emul_check_aligned(smem, 16); pcu_emul_check_aligned(gmem, 16);
+  if (bytes % 16) std::abort();
+  std::memcpy(smem, gmem, bytes);
+}
+inline bool mbar_try_wait(unsigned long long*, unsigned) { return true; }
+inline void pcu_trap() { std::abort(); }
+#endif
+
+// Same mapping and summation order as spmm_kernel<T, CPL>.  The col/val chunk of the row block lands in shared memory
+// through two cp.async.bulk copies issued by one thread (no register round trip, no 6 rounds of LDG + STS by the whole
+// CTA), completion on an mbarrier; the chunk starts are aligned down to 16 bytes (oc / ov entries of slack in front)
+// and the sizes rounded up (the device arrays carry 16 bytes of slack at the end).  HALO = false (no column >= m: one
+// process, or the local part of the overlapped product) drops the "block row or halo row" select, so the row phase is
+// LDS + LDS + IMAD.WIDE + LDG + CPL DFMA per entry.  Needs ldx == T and every row block within the staging capacity.
+template <int T, int CPL, bool HALO>
+__global__ void __launch_bounds__(kThreads, CPL == 4 ? 6 : 8) spmm_bulk_kernel(SpmmArgs a) {  // <= 40 / 32 registers, no spills
+
+  static_assert(CPL == 2 || CPL == 4, "lanes own 2 or 4 adjacent columns");
+  constexpr int G = T / CPL;
+  constexpr int NG = kThreads / G;
+  constexpr int kCap = kShapeNnz[0];
+  __shared__ __align__(16) int s_col[kCap + 8];
+  __shared__ __align__(16) double s_val[kCap + 4];
+  __shared__ int s_rp[kShapeRows[0] + 1];
+  __shared__ __align__(8) unsigned long long s_bar;
+
+  const int4 d = __ldg(a.blk + blockIdx.x);
+  const int r0 = d.x, r1 = d.y, p0 = d.z, p1 = d.w;
+  const int tid = threadIdx.x;
+  const int pc = p0 & ~3, pv = p0 & ~1;  // 16-byte aligned starts of the two chunks
+  const unsigned bc = (unsigned)(((p1 - pc) * 4 + 15) & ~15), bv = (unsigned)(((p1 - pv) * 8 + 15) & ~15);
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0 && p1 > p0) {
+    mbar_arrive_expect_tx(&s_bar, bc + bv);
+    bulk_g2s(s_col, a.colInd + pc, bc, &s_bar);
+    bulk_g2s(s_val, a.val + pv, bv, &s_bar);
+  }
+  for (int i = tid; i <= r1 - r0; i += kThreads) s_rp[i] = __ldg(a.rowPtr + r0 + i) - p0;
+  __syncthreads();
+  if (p1 > p0) {  // bounded wait: a lost transaction traps instead of hanging the GPU
+    unsigned spins = 0;
+    while (!mbar_try_wait(&s_bar, 0))
+      if (++spins > (1u << 26)) pcu_trap();
+  }
+  const int oc = p0 - pc, ov = p0 - pv;
+  const int grp = tid / G, lig = tid % G;
+  const double* xl = a.X + CPL * lig;
+  const double* hl = HALO ? a.H + CPL * lig - (size_t)a.m * T : nullptr;  // halo row c - m at hl + c * T
+  for (int r = r0 + grp; r < r1; r += NG) {
+    const int b = s_rp[r - r0], e = s_rp[r - r0 + 1];
+    double acc[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) acc[j] = 0.0;
+#pragma unroll 4
+    for (int p = b; p < e; ++p) {
+      const int c = s_col[oc + p];
+      const double v = s_val[ov + p];
+      const double* src = ((HALO && c >= a.m) ? hl : xl) + (size_t)c * T;
+      if constexpr (CPL == 4) {
+        double x[4];
+        ldg4(src, x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fma(v, x[j], acc[j]);
+      } else {
+        const double2 x = ldg2(src);
+        acc[0] = fma(v, x.x, acc[0]);
+        acc[1] = fma(v, x.y, acc[1]);
+      }
+    }
+    double* dst = a.Y + (size_t)r * a.ldy + CPL * lig;
+    if constexpr (CPL == 4) {
+      stg4(dst, acc);
+    } else {
+      *reinterpret_cast<double2*>(dst) = make_double2(acc[0], acc[1]);
+    }
+  }
+}
+
 // any 1 <= t <= 32: 16 lanes per row, lane owns columns lig and lig+16
 __global__ void __launch_bounds__(kThreads) spmm_kernel_generic(SpmmArgs a) {
   constexpr int G = 16, NG = kThreads / G;

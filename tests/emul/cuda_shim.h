@@ -28,6 +28,7 @@ void __syncthreads();
 #define __forceinline__ inline
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }

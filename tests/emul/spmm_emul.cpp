@@ -38,8 +38,12 @@ void emul_run_block(int block, void (*thunk)(void*), void* ctx) {
 
 namespace {
 
+// variant codes of the tests: 0 default kernel, 1 / 2 / 4 lean with that many gathers in flight, 8 / 9 bulk-copy staging
+// (9: HALO = false, for operators without a column >= m)
 template <int T, int CPL>
 void run_variant(int lean, const SpmmArgs& a, int nblk) {
+  if (lean == 8) { emul_launch(nblk, kThreads, [&] { spmm_bulk_kernel<T, CPL, true>(a); }); return; }
+  if (lean == 9) { emul_launch(nblk, kThreads, [&] { spmm_bulk_kernel<T, CPL, false>(a); }); return; }
   if (lean >= 4) emul_launch(nblk, kThreads, [&] { spmm_lean_kernel<T, CPL, 4, 4>(a); });
   else if (lean >= 2) emul_launch(nblk, kThreads, [&] { spmm_lean_kernel<T, CPL, 2, 5>(a); });
   else if (lean == 1) emul_launch(nblk, kThreads, [&] { spmm_lean_kernel<T, CPL, 1, 0>(a); });
@@ -56,7 +60,17 @@ int run_spmm(int lean, int cpl, int m, const int* rowPtr, const int* colInd, con
     if (t < 8 || ldx != t) return 2;
     for (const int4& b : blk) if (b.w - b.z > kShapeNnz[0]) return 3;  // the host would not choose the lean kernel
   }
-  SpmmArgs a{rowPtr, colInd, val, blk.data(), m, X, ldx, H, Y, ldy, t};
+  // like upload_csr: 16 bytes of slack behind the entries (the bulk copies round their size up), 16-byte aligned starts
+  const int nnz = rowPtr[m];
+  std::vector<double> vbuf((size_t)nnz + 6);
+  std::vector<int> cbuf((size_t)nnz + 12);
+  double* vpad = vbuf.data() + ((16 - reinterpret_cast<uintptr_t>(vbuf.data()) % 16) % 16) / 8;
+  int* cpad = cbuf.data() + ((16 - reinterpret_cast<uintptr_t>(cbuf.data()) % 16) % 16) / 4;
+  std::memcpy(vpad, val, sizeof(double) * (size_t)nnz);
+  std::memcpy(cpad, colInd, sizeof(int) * (size_t)nnz);
+  for (int k = 0; k < 2; ++k) vpad[nnz + k] = std::nan("");
+  for (int k = 0; k < 4; ++k) cpad[nnz + k] = -123456789;
+  SpmmArgs a{rowPtr, cpad, vpad, blk.data(), m, X, ldx, H, Y, ldy, t};
   const int nblk = (int)blk.size();
   if (cpl == 0) { emul_launch(nblk, kThreads, [&] { spmm_kernel_generic(a); }); return 0; }
   if (t == 1 && cpl == 1 && lean == 0) { emul_launch(nblk, kThreads, [&] { spmm_kernel<1, 1>(a); }); return 0; }

@@ -64,8 +64,8 @@ candidates = pytest.mark.skipif(not os.environ.get("PREALPS_TEST_CANDIDATES"),
 @candidates
 @pytest.mark.parametrize("gen,N", [("poisson7", 14), ("stencil27", 9)])
 def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
-    """PREALPS_SPMM_LEAN=1|2|4 (spmm_lean_kernel, 1, 2 or 4 gathers in flight per lane) keeps the mapping and the summation
-    order: same bits as the default kernel"""
+    """PREALPS_SPMM_LEAN=1|2|4 (spmm_lean_kernel, 1, 2 or 4 gathers in flight per lane) and PREALPS_SPMM_BULK=1
+    (spmm_bulk_kernel, cp.async.bulk staging) keep the mapping and the summation order: same bits as the default kernel"""
     A = getattr(gen_matrices, gen)(N).tocsr()
     m = A.shape[0]
     nh = 53
@@ -74,8 +74,9 @@ def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
     Aext.sort_indices()
     rng = np.random.default_rng(1)
     out = {}
-    for lean in ("0", "1", "2", "4"):
-        monkeypatch.setenv("PREALPS_SPMM_LEAN", lean)
+    for lean in ("0", "1", "2", "4", "bulk"):
+        monkeypatch.setenv("PREALPS_SPMM_LEAN", "0" if lean == "bulk" else lean)
+        monkeypatch.setenv("PREALPS_SPMM_BULK", "1" if lean == "bulk" else "0")
         op = C.c_void_p()
         assert cu.pcu_spmm_create(dev.ctx, m, nh, capi.ip(Aext.indptr.astype(np.int32)), capi.ip(Aext.indices.astype(np.int32)),
                                   capi.dp(Aext.data), C.byref(op)) == 0, cu.pcu_last_error()
@@ -95,7 +96,7 @@ def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
             dev.free(dX, dY)
         cu.pcu_spmm_destroy(op)
     for t in (8, 16, 32):
-        for lean in ("1", "2", "4"):
+        for lean in ("1", "2", "4", "bulk"):
             assert np.array_equal(out["0", t], out[lean, t])
 
 

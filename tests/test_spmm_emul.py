@@ -117,12 +117,29 @@ def test_lean_candidates_are_bit_identical(emul, gen, N, t, cpl):
     base = run(emul, "merged", 0, cpl, m, rp, ci, v, X, H, t, t)
     ref = Aext @ np.vstack([X, H])
     assert np.allclose(base, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
-    for lean in (1, 2, 4):
+    for lean in (1, 2, 4, 8):  # 8: PREALPS_SPMM_BULK=1, cp.async.bulk staging (HALO = true)
         Y = run(emul, "merged", lean, cpl, m, rp, ci, v, X, H, t, t)
         assert np.array_equal(Y, base), (lean, np.abs(Y - base).max())
 
 
-@pytest.mark.parametrize("t,cpl,lean", [(1, 1, 0), (4, 2, 0), (8, 4, 0), (8, 4, 1), (16, 2, 4), (32, 4, 2), (12, 0, 0)])
+@pytest.mark.parametrize("t,cpl", [(8, 2), (8, 4), (16, 4), (32, 2)])
+def test_bulk_candidate_without_halo(emul, t, cpl):
+    """spmm_bulk_kernel<T, CPL, false>: one process (no column >= m); every alignment of a row block's first entry"""
+    A = gen_matrices.poisson7(9).tolil()
+    A[3, :] = 0  # an empty row and rows of odd length move the chunk starts over all residues mod 4
+    A[5, 100:111] = 1.5
+    A = A.tocsr()
+    A.sort_indices()
+    m = A.shape[0]
+    rp, ci, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    X, H = inputs(m, 1, t, t, 3 * t)
+    base = run(emul, "merged", 0, cpl, m, rp, ci, v, X, H, t, t)
+    assert np.allclose(base, A @ X, rtol=1e-13, atol=1e-13)
+    Y = run(emul, "merged", 9, cpl, m, rp, ci, v, X, H, t, t)
+    assert np.array_equal(Y, base)
+
+
+@pytest.mark.parametrize("t,cpl,lean", [(1, 1, 0), (4, 2, 0), (8, 4, 0), (8, 4, 1), (16, 2, 4), (32, 4, 2), (12, 0, 0), (8, 4, 9), (16, 2, 9)])
 def test_local_halo_split_is_bit_identical(emul, t, cpl, lean):
     """PREALPS_SPMM_OVERLAP=1: local kernel on the entries with column < m, then halo_add_kernel continues the FMA chains"""
     Aext, m, rp, ci, v = operator("poisson7", 11, 37)

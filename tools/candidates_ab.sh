@@ -15,6 +15,7 @@ python tools/spmm_sweep.py 128 > $out/cand_spmm_default.jsonl 2> $out/cand_spmm_
 for nb in 1 2 4; do  # gathers in flight per lane
   PREALPS_SPMM_LEAN=$nb python tools/spmm_sweep.py 128 > $out/cand_spmm_lean$nb.jsonl 2> $out/cand_spmm_lean$nb.err
 done
+PREALPS_SPMM_BULK=1 python tools/spmm_sweep.py 128 > $out/cand_spmm_bulk.jsonl 2> $out/cand_spmm_bulk.err
 # block-Jacobi apply, 8 subdomains of 64^3 on this GPU (the N=1 bench) and ONE 64^3 subdomain (what each GPU holds at N=8)
 python tools/variants.py 128 8 8 > $out/cand_bj.log 2>&1
 python tools/variants.py 64 1 8 >> $out/cand_bj.log 2>&1

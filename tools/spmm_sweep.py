@@ -17,5 +17,5 @@ for kind, name in ((1, "stencil27"), (0, "poisson7")):
         capi.lib.preAlps_b200_BenchKernel(0, t, 10, 1, C.byref(ms))
         b = capi.stat("spmm_bytes_t%d" % t)
         gbs = b / ms.value / 1e6
-        print(json.dumps({"operator": "%s %d^3" % (name, n), "lean": os.environ.get("PREALPS_SPMM_LEAN", "0"), "t": t, "us": round(ms.value * 1e3, 2), "algorithmic_MB": round(b / 1e6, 1),
+        print(json.dumps({"operator": "%s %d^3" % (name, n), "lean": os.environ.get("PREALPS_SPMM_LEAN", "0"), "bulk": os.environ.get("PREALPS_SPMM_BULK", "0"), "t": t, "us": round(ms.value * 1e3, 2), "algorithmic_MB": round(b / 1e6, 1),
                           "GB/s": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 3), "frac_of_8TBs": round(gbs / 8000, 3)}), flush=True)
