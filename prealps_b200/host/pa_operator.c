@@ -205,21 +205,30 @@ static int finish_build(void) {
 static int partition_global(CPLM_Mat_CSR_t* G, int S, int s_lo, int s_hi, int scale, const int* parts_in) {
   pa_state_t* g = &pa_g;
   const int M = G->info.m;
+  const int timing = getenv("PREALPS_B200_TIMING") != NULL;
+  double t0 = pa_wtime(), t1;
+#define PA_LAP(what) do { if (timing) { t1 = pa_wtime(); fprintf(stderr, "[prealps_b200] setup: %-28s %.3f s\n", what, t1 - t0); t0 = t1; } } while (0)
   if (scale) pa_sym_scale(G);
+  PA_LAP("symmetric max-scaling");
   int* parts = (int*)pa_xmalloc(sizeof(int) * (size_t)M);
   if (parts_in) memcpy(parts, parts_in, sizeof(int) * (size_t)M);
   else if (pa_kway_parts(G, S, parts)) CPLM_Abort("METIS k-way partitioning failed");
+  PA_LAP("METIS k-way partition");
   g->rowPos = (int*)pa_xmalloc(sizeof(int) * ((size_t)S + 1));
   g->nrowPos = S + 1;
   g->perm = (int*)pa_xmalloc(sizeof(int) * (size_t)M);
   g->nperm = M;
   pa_parts_to_perm(M, parts, S, g->rowPos, g->perm);
   free(parts);
+  PA_LAP("parts -> permutation");
   CPLM_Mat_CSR_t P = CPLM_MatCSRNULL();
   pa_permute_sym(G, g->perm, &P);
   CPLM_MatCSRFree(G);
+  PA_LAP("symmetric permutation");
   pa_row_panel(&P, g->rowPos[s_lo], g->rowPos[s_hi], &g->A);
   CPLM_MatCSRFree(&P);
+  PA_LAP("row panel");
+#undef PA_LAP
   return 0;
 }
 
