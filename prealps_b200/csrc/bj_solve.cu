@@ -29,8 +29,13 @@ constexpr int kWarps = kThreads / 32;
 // level). Each is launched with programmatic stream serialization, so its CTAs may start while the previous
 // kernel drains: they fetch what does not depend on it (work units, panel descriptors, the first panel data), then
 // wait here for the previous kernel to complete. Without the launch attribute both instructions are no-ops.
+#ifndef PCU_EMUL
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else  // tests/emul runs the kernels of a stream one after the other
+inline void pdl_wait() {}
+inline void pdl_launch_dependents() {}
+#endif
 
 // ---- forward right-hand-side assembly: one group of G lanes per column
 // PREFETCH (opt-in, PREALPS_BJ_ASM_PREFETCH=1; written after the last GPU session of round 1, not measured yet): a
@@ -114,6 +119,7 @@ struct SweepArgs {
 // one 256-bit load per lane (SASS LDG.E.NA.EFL2.256): the 32 bytes a lane owns of a k-block, not allocated in L1 and
 // first in line for eviction from L2 -- the panels are streamed once per apply (19 GB) and must not push the block
 // vectors (update rows, ancestor rows gathered by the backward sweep) out of the 126 MB L2
+#ifndef PCU_EMUL
 __device__ __forceinline__ void ld_stream4(const double* p, double2& a, double2& b) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
                : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
@@ -134,16 +140,50 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else  // tests/emul: the same data movement without the cache hints; cp.async completes at once
+inline void ld_stream4(const double* p, double2& a, double2& b) {
+  pcu_emul_check_aligned(p, 32);
+  a = make_double2(p[0], p[1]);
+  b = make_double2(p[2], p[3]);
+}
+inline unsigned long long l2_evict_first_policy() { return 0; }
+inline void cp_async16(void* smem_dst, const void* gmem_src) {
+  pcu_emul_check_aligned(smem_dst, 16);
+  pcu_emul_check_aligned(gmem_src, 16);
+  std::memcpy(smem_dst, gmem_src, 16);
+}
+inline void cp_async16_stream(void* smem_dst, const void* gmem_src, unsigned long long) { cp_async16(smem_dst, gmem_src); }
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
+#endif
 
 // rows of the input block staged per tile and per warp (4 KB per buffer at any T)
 template <int T>
 struct Tile { static constexpr int KT = (T <= 8) ? 64 : (512 / T); };  // k steps per tile, even, KT*T*8 = 4 KB for T >= 8
 
 
+#ifndef PCU_EMUL
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+#define PCU_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+#else
+// D (8x8) += A (8x4, row-major fragment: lane holds A[lane/4][lane%4]) * B (4x8, lane holds B[lane%4][lane/4]);
+// lane holds D[lane/4][2*(lane%4) + {0,1}]
+inline void dmma884(double& d0, double& d1, double a, double b) {
+  double A[32], B[32];
+  emul_warp_allgather(a, A);
+  emul_warp_allgather(b, B);
+  const int lane = (int)(threadIdx.x & 31), row = lane >> 2, n0 = 2 * (lane & 3);
+  for (int k = 0; k < 4; ++k) {
+    d0 = fma(A[row * 4 + k], B[n0 * 4 + k], d0);
+    d1 = fma(A[row * 4 + k], B[(n0 + 1) * 4 + k], d1);
+  }
+}
+#define PCU_DYN_SMEM(name) double* name = static_cast<double*>(emul_dyn_smem())
+#endif
 
 // lane owns, for every row group rg and column block nb: row row0 + 8*rg + lane/4, columns 8*nb + 2*(lane%4) + {0,1}
 template <int T, bool FWD>
@@ -198,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
   constexpr int KB = KT / 4;            // k-blocks per tile
   constexpr int TILE = KT * T;          // doubles per tile buffer
   static_assert(KB % D == 0, "ring depth must divide the k-blocks of a tile");
-  extern __shared__ __align__(16) double smem[];
+  PCU_DYN_SMEM(smem);
   double* red = smem;                   // 32 * T doubles
   const WorkUnit u = a.units[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -369,7 +409,7 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
   constexpr int NB = (T + 7) / 8;
   constexpr int MB = KMAX * 32;         // doubles of panel data per warp
   constexpr int BB = KMAX * T;          // doubles of input rows per warp
-  extern __shared__ __align__(16) double smem[];
+  PCU_DYN_SMEM(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lr = lane >> 2, lk = lane & 3;
   const int q = blockIdx.x * WARPS + warp;

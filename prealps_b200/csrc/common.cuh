@@ -1,6 +1,10 @@
 // common.cuh -- shared declarations for libprealps_cuda (sm_100a only).
 #pragma once
+#ifdef PCU_EMUL  // tests/emul: CPU emulation of the kernels (test infrastructure, never defined for the product build)
+#include "cuda_emul.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdint>
 #include <cstdio>

@@ -1,0 +1,120 @@
+// cuda_emul.cpp -- TEST INFRASTRUCTURE ONLY: the execution engine behind cuda_emul.h.
+#include "cuda_emul.h"
+
+thread_local dim3 threadIdx;
+dim3 blockIdx, blockDim, gridDim;
+
+namespace {
+
+// barrier whose participants may leave for good (a CUDA thread that returns stops counting)
+struct DropBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int expected = 0, arrived = 0;
+  unsigned gen = 0;
+  void reset(int n) { expected = n; arrived = 0; }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned g = gen;
+    if (++arrived >= expected) { arrived = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+  void drop() {
+    std::unique_lock<std::mutex> lk(m);
+    --expected;
+    if (expected > 0 && arrived >= expected) { arrived = 0; ++gen; cv.notify_all(); }
+  }
+};
+
+constexpr int kMaxWarps = 32;
+DropBarrier g_block_bar;
+DropBarrier g_warp_bar[kMaxWarps];
+double g_warp_buf[kMaxWarps][32];
+char* g_dyn = nullptr;
+thread_local int t_warp = 0, t_lane = 0;
+
+struct Launch {
+  const std::function<void()>* body;
+  int nthreads;
+  pthread_barrier_t start, done;
+  bool stop = false;
+};
+
+struct WorkerArg { Launch* L; int tid; };
+
+void* worker(void* p) {
+  WorkerArg* a = static_cast<WorkerArg*>(p);
+  Launch* L = a->L;
+  threadIdx = dim3((unsigned)a->tid, 0, 0);
+  t_warp = a->tid / 32;
+  t_lane = a->tid % 32;
+  for (;;) {
+    pthread_barrier_wait(&L->start);
+    if (L->stop) break;
+    (*L->body)();
+    g_warp_bar[t_warp].drop();
+    g_block_bar.drop();
+    pthread_barrier_wait(&L->done);
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+void __syncthreads() { g_block_bar.wait(); }
+void __syncwarp(unsigned) { g_warp_bar[t_warp].wait(); }
+void* emul_dyn_smem() { return g_dyn; }
+
+void emul_warp_allgather(double v, double (&all)[32]) {
+  g_warp_buf[t_warp][t_lane] = v;
+  g_warp_bar[t_warp].wait();
+  for (int i = 0; i < 32; ++i) all[i] = g_warp_buf[t_warp][i];
+  g_warp_bar[t_warp].wait();
+}
+
+void emul_launch_impl(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body) {
+  if (block.y != 1 || block.z != 1 || block.x == 0 || block.x > 32u * kMaxWarps) {
+    std::fprintf(stderr, "[emul] unsupported block shape %u x %u x %u\n", block.x, block.y, block.z);
+    std::abort();
+  }
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+  const int nthreads = (int)block.x;
+  gridDim = grid;
+  blockDim = block;
+  void* dyn = nullptr;
+  if (posix_memalign(&dyn, 128, dyn_smem + 128) != 0) std::abort();
+  g_dyn = static_cast<char*>(dyn);
+  Launch L;
+  L.body = &body;
+  L.nthreads = nthreads;
+  pthread_barrier_init(&L.start, nullptr, (unsigned)nthreads + 1);
+  pthread_barrier_init(&L.done, nullptr, (unsigned)nthreads + 1);
+  std::vector<pthread_t> th(nthreads);
+  std::vector<WorkerArg> args(nthreads);
+  pthread_attr_t at;
+  pthread_attr_init(&at);
+  pthread_attr_setstacksize(&at, 512 * 1024);
+  for (int i = 0; i < nthreads; ++i) {
+    args[i] = WorkerArg{&L, i};
+    if (pthread_create(&th[i], &at, worker, &args[i]) != 0) { std::perror("pthread_create"); std::abort(); }
+  }
+  const int nwarps = (nthreads + 31) / 32;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        blockIdx = dim3(bx, by, bz);
+        std::memset(g_dyn, 0xEE, dyn_smem);
+        g_block_bar.reset(nthreads);
+        for (int w = 0; w < nwarps; ++w) g_warp_bar[w].reset(std::min(32, nthreads - 32 * w));
+        pthread_barrier_wait(&L.start);
+        pthread_barrier_wait(&L.done);
+      }
+  L.stop = true;
+  pthread_barrier_wait(&L.start);
+  for (int i = 0; i < nthreads; ++i) pthread_join(th[i], nullptr);
+  pthread_attr_destroy(&at);
+  pthread_barrier_destroy(&L.start);
+  pthread_barrier_destroy(&L.done);
+  std::free(dyn);
+  g_dyn = nullptr;
+}

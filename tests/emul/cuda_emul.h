@@ -1,0 +1,141 @@
+// cuda_emul.h -- TEST INFRASTRUCTURE ONLY: a miniature CUDA execution model and runtime on the CPU, enough to run
+// prealps_b200/csrc/bj_factor.cu and bj_solve.cu (the block-Jacobi factorisation and sweeps) unmodified apart from their
+// PCU_EMUL branches (inline PTX -> plain C++).  One pthread per CUDA thread, blocks of a grid one after the other,
+// __syncthreads / __syncwarp as barriers that tolerate threads which have already returned, mma.sync.m8n8k4.f64 as a
+// warp-wide exchange.  "Device" memory is host memory; streams, events and launch attributes are accepted and ignored.
+// It checks index logic and data flow (who reads what after which barrier is NOT checked: cp.async completes at
+// once, griddepcontrol is a no-op).  Never linked into the product libraries: tests/test_bj_emul.py builds it.
+#pragma once
+#include <pthread.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <vector>
+
+// ---------------------------------------------------------------- vector types, qualifiers
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct int4 { int x, y, z, w; };
+struct __attribute__((aligned(16))) double2 { double x, y; };
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+
+extern thread_local dim3 threadIdx;
+extern dim3 blockIdx, blockDim, gridDim;
+
+void __syncthreads();
+void __syncwarp(unsigned mask = 0xffffffffu);
+inline void __threadfence() {}
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicMax(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+template <class T> inline T __ldcg(const T* p) { return *p; }
+inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+using std::fma;
+using std::max;
+using std::min;
+void* emul_dyn_smem();
+// every lane of the calling warp contributes v; all[0..31] receives the 32 values (lanes that have returned: 0)
+void emul_warp_allgather(double v, double (&all)[32]);
+
+// values that fit a double exactly (the kernels shuffle small ints)
+template <class T> inline T __shfl_sync(unsigned, T v, int src_lane) {
+  double all[32];
+  emul_warp_allgather((double)v, all);
+  return (T)all[src_lane & 31];
+}
+
+inline void pcu_emul_check_aligned(const void* p, size_t a) {
+  if (reinterpret_cast<uintptr_t>(p) % a != 0) {
+    std::fprintf(stderr, "[emul] misaligned %zu-byte vector access at %p\n", a, p);
+    std::abort();
+  }
+}
+
+// ---------------------------------------------------------------- runtime
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+struct emul_event { double t; };
+typedef emul_event* cudaEvent_t;
+constexpr cudaError_t cudaSuccess = 0;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaStreamCaptureModeThreadLocal = 1 };
+enum { cudaLaunchAttributeProgrammaticStreamSerialization = 6 };
+struct cudaLaunchAttribute {
+  int id;
+  struct { int programmaticStreamSerializationAllowed; } val;
+};
+struct cudaLaunchConfig_t {
+  dim3 gridDim, blockDim;
+  size_t dynamicSmemBytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaLaunchAttribute* attrs = nullptr;
+  unsigned numAttrs = 0;
+};
+
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
+  void* q = nullptr;
+  if (posix_memalign(&q, 256, bytes ? bytes : 256) != 0) return 2;
+  std::memset(q, 0xEE, bytes ? bytes : 256);  // fresh device memory is garbage
+  *p = static_cast<T*>(q);
+  return cudaSuccess;
+}
+inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { if (n) std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+inline double emul_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emul_event{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = emul_now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)((b->t - a->t) * 1e3); return cudaSuccess; }
+// CUDA graphs are not emulated: capture reports failure, the caller falls back to plain launches
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return 1; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return 1; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, int) { return 1; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return 1; }
+
+// run body() for every thread of every block
+void emul_launch_impl(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body);
+template <class F>
+inline void emul_launch(dim3 grid, dim3 block, size_t dyn_smem, F body) { emul_launch_impl(grid, block, dyn_smem, std::function<void()>(body)); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(KArgs...), Args... args) {
+  emul_launch(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [=] { kernel(KArgs(args)...); });
+  return cudaSuccess;
+}
