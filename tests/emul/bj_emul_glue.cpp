@@ -18,4 +18,5 @@ extern "C" {
 const char* pcu_last_error(void) { return pcu::g_err; }
 pcu_ctx* emul_ctx_create(void) { return new pcu_ctx(); }
 long long emul_launch_count(pcu_ctx* c) { return c->launches; }
+long long emul_graph_replay_count(void) { return emul_graph_replays; }
 }

@@ -3,6 +3,20 @@
 
 thread_local dim3 threadIdx;
 dim3 blockIdx, blockDim, gridDim;
+long long emul_graph_replays = 0;
+static emul_graph* g_capture = nullptr;  // non-null while a stream capture is open
+static bool g_replaying = false;
+
+cudaError_t cudaStreamBeginCapture(cudaStream_t, int) {
+  if (g_capture) return 1;
+  g_capture = new emul_graph();
+  return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) {
+  *g = g_capture;
+  g_capture = nullptr;
+  return *g ? cudaSuccess : 1;
+}
 
 namespace {
 
@@ -78,6 +92,12 @@ void emul_launch_impl(dim3 grid, dim3 block, size_t dyn_smem, const std::functio
     std::abort();
   }
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return;
+  if (g_capture) {  // record: the body owns copies of the kernel arguments
+    const std::function<void()> copy = body;
+    g_capture->launches.push_back([=] { g_replaying = true; emul_launch_impl(grid, block, dyn_smem, copy); g_replaying = false; });
+    return;
+  }
+  if (g_replaying) ++emul_graph_replays;
   const int nthreads = (int)block.x;
   gridDim = grid;
   blockDim = block;

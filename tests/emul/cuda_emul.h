@@ -78,8 +78,6 @@ inline void pcu_emul_check_aligned(const void* p, size_t a) {
 // ---------------------------------------------------------------- runtime
 typedef int cudaError_t;
 typedef void* cudaStream_t;
-typedef void* cudaGraph_t;
-typedef void* cudaGraphExec_t;
 struct emul_event { double t; };
 typedef emul_event* cudaEvent_t;
 constexpr cudaError_t cudaSuccess = 0;
@@ -121,13 +119,17 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSucces
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = emul_now(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)((b->t - a->t) * 1e3); return cudaSuccess; }
-// CUDA graphs are not emulated: capture reports failure, the caller falls back to plain launches
-inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return 1; }
-inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return 1; }
-inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, int) { return 1; }
-inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
-inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
-inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return 1; }
+// CUDA graphs: a capture records the launches (with their arguments) instead of running them, a graph launch replays them
+struct emul_graph { std::vector<std::function<void()>> launches; };
+typedef emul_graph* cudaGraph_t;
+typedef emul_graph* cudaGraphExec_t;
+cudaError_t cudaStreamBeginCapture(cudaStream_t, int);
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g);
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, int) { *e = new emul_graph(*g); return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) { for (auto& f : e->launches) f(); return cudaSuccess; }
+extern long long emul_graph_replays;  // kernels run from a graph launch (tests)
 
 // run body() for every thread of every block
 void emul_launch_impl(dim3 grid, dim3 block, size_t dyn_smem, const std::function<void()>& body);

@@ -109,3 +109,45 @@ def test_indefinite_block_is_rejected(emul):
     A[5, 5] = -3.0
     rc, bj, cuts, blocks = factor(emul, A.tocsr(), 1)
     assert rc == 2 and b"not positive definite" in lib.pcu_last_error()
+
+
+def test_graph_candidate_replays_the_same_chain(emul, monkeypatch):
+    """PREALPS_BJ_GRAPH=1: first use of an argument tuple runs directly, the second captures + launches, later ones replay;
+    growing the work vectors (a wider solve) drops the captured graphs"""
+    lib, ctx = emul
+    lib.emul_graph_replay_count.restype = C.c_longlong
+    lib.emul_launch_count.restype = C.c_longlong
+    A = gen_matrices.poisson7(5).tocsr()
+    n = A.shape[0]
+    rc, bj, cuts, blocks = factor(emul, A, 1)
+    assert rc == 0
+    B4 = np.random.default_rng(4).standard_normal((n, 4))
+    X4 = np.zeros((n, 4))
+    monkeypatch.delenv("PREALPS_BJ_GRAPH", raising=False)
+    assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0
+    base, l0 = X4.copy(), lib.emul_launch_count(ctx)
+    assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0
+    per_apply = lib.emul_launch_count(ctx) - l0
+    monkeypatch.setenv("PREALPS_BJ_GRAPH", "1")
+    r0 = lib.emul_graph_replay_count()
+    for k in range(4):
+        X4[:] = 0
+        l0 = lib.emul_launch_count(ctx)
+        assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0, lib.pcu_last_error()
+        assert np.array_equal(X4, base)
+        assert lib.emul_launch_count(ctx) - l0 == per_apply  # the launch counter keeps counting kernels
+        replays = lib.emul_graph_replay_count() - r0
+        assert (replays == 0) if k == 0 else (replays > 0)
+        r0 = lib.emul_graph_replay_count()
+    # a wider solve re-allocates the work vectors: the old graph must not be replayed into freed memory
+    B16 = np.random.default_rng(16).standard_normal((n, 16))
+    X16 = np.zeros((n, 16))
+    for k in range(3):
+        assert lib.pcu_bj_apply(bj, dp(B16), 16, dp(X16), 16, 16) == 0
+    ref = direct(blocks, cuts, B16)
+    assert np.linalg.norm(X16 - ref) <= 1e-12 * np.linalg.norm(ref)
+    for k in range(3):
+        X4[:] = 0
+        assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0
+        assert np.array_equal(X4, base)
+    lib.pcu_bj_destroy(bj)
