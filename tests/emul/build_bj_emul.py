@@ -53,7 +53,7 @@ def build():
     open(gen2, "w").write('#define PCU_EMUL 1\n#include "%s"\n' % os.path.join(CSRC, "bj_solve.cu"))
     cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I" + EMUL, "-I" + CSRC,
            gen, gen2, os.path.join(CSRC, "bj_symbolic.cpp"), os.path.join(EMUL, "cuda_emul.cpp"),
-           os.path.join(EMUL, "bj_emul_glue.cpp"), METIS_A, "-o", so, "-lm"]
+           os.path.join(EMUL, "bj_emul_glue.cpp"), METIS_A, "-o", so, "-lm", "-Wl,-Bsymbolic", "-Wl,--exclude-libs=ALL"]  # own symbols first: the product library may be loaded RTLD_GLOBAL
     subprocess.check_call(cmd)
     return so
 
