@@ -50,6 +50,12 @@ constexpr int kChunkMinKB = 128;            // shortest slice (k-blocks of 4 ste
 constexpr int kTinyFold = 512;              // fewer short panels than this at a level: no separate launch for them
 constexpr int kWarpSlots = 148 * 2 * 8;     // resident warps of the sweep kernel (2 CTAs of 8 warps per SM)
 
+struct BottomLevel {   // one (subtree, level) of the bottom-of-the-forest launch: ranges into bot_cols / bot_fp / bot_bp
+  int c0, c1;          // forest columns to assemble
+  int f0, f1;          // forward panels
+  int b0, b1;          // backward panels
+};
+
 struct WorkUnit {      // one CTA of the sweep kernels
   int first;           // first panel
   int count;           // 1..8 panels (one per warp), or 1 panel split over all warps when split != 0
@@ -101,6 +107,13 @@ struct pcu_bj {
   double* scratch = nullptr;
   int* counters = nullptr;
   int scratch_slots = 0, ncounters = 0;
+  // opt-in (PREALPS_BJ_BOTTOM=Lc at creation): levels [0, Lc) of the forest as ONE forward and ONE backward launch, a CTA
+  // per subtree hanging below level Lc (bj_solve.cu: bottom_kernel)
+  int bottom = 0, nsubtrees = 0;
+  pcu::BottomLevel* bot_lv = nullptr;  // nsubtrees * bottom entries, subtree-major
+  int* bot_cols = nullptr;
+  int* bot_fp = nullptr;
+  int* bot_bp = nullptr;
   // opt-in (PREALPS_BJ_GRAPH=1): the launch chain of one apply, captured once per argument tuple and replayed
   struct ApplyGraph {
     const double* B; int ldb; double* X; int ldx; int t;

@@ -359,6 +359,7 @@ int pcu_bj_destroy(pcu_bj* bj) {
   cudaFree(bj->fwd_data); cudaFree(bj->bwd_data); cudaFree(bj->fwd_panels); cudaFree(bj->bwd_panels);
   cudaFree(bj->fwd_units); cudaFree(bj->bwd_units); cudaFree(bj->perm); cudaFree(bj->rows);
   cudaFree(bj->lvl_cols); cudaFree(bj->gl_ptr); cudaFree(bj->gl_idx);
+  cudaFree(bj->bot_lv); cudaFree(bj->bot_cols); cudaFree(bj->bot_fp); cudaFree(bj->bot_bp);
   cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp); cudaFree(bj->scratch); cudaFree(bj->counters);
   delete bj;
   return 0;
@@ -533,6 +534,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   // panels (sorted by level, long panels first inside a level), work units, gather lists
   std::vector<FwdPanel> fp;
   std::vector<BwdPanel> bp;
+  std::vector<int> fp_sn, bp_sn;  // supernode of every panel
   std::vector<WorkUnit> fu, bu;
   bj->fwd_unit_ptr.assign(nlev + 1, 0);
   bj->fwd_lvl_bytes.assign(nlev, 0.0);
@@ -616,6 +618,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       fdoubles += (long long)e.first * 32;
       bj->fwd_lvl_bytes[l] += 8.0 * e.first * 32;
       fp.push_back(P);
+      fp_sn.push_back(s);
     }
     kl.resize(fp.size());
     for (size_t i = f0; i < fp.size(); ++i) kl[i] = fp[i].klen;
@@ -641,6 +644,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       bdoubles += (long long)e.first * 32;
       bj->bwd_lvl_bytes[l] += 8.0 * e.first * 32;
       bp.push_back(P);
+      bp_sn.push_back(s);
     }
     kl.assign(bp.size(), 0);
     for (size_t i = b0; i < bp.size(); ++i) kl[i] = bp[i].klen;
@@ -670,6 +674,50 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     for (int s = 0; s < ns; ++s)  // ascending supernode order => fixed summation order
       for (int i = sn_w[s]; i < sn_h[s]; ++i) gl_idx[fill[rows[sn_rp[s] + i]]++] = uoff[s] + (i - sn_w[s]);
   }
+  // bottom of the forest as one launch per direction (opt-in): every supernode below level Lc belongs to the subtree of its
+  // highest ancestor that is still below Lc; all its descendants, hence everything its columns gather, are in that subtree
+  std::vector<BottomLevel> bot_lv;
+  std::vector<int> bot_cols, bot_fp, bot_bp;
+  if (const char* e = getenv("PREALPS_BJ_BOTTOM")) bj->bottom = std::max(0, std::min(atoi(e), nlev));
+  if (bj->bottom > 0) {
+    const int Lc = bj->bottom;
+    std::vector<int> root(ns, -1), sub_of(ns, -1);
+    int nsub = 0;
+    for (int s = 0; s < ns; ++s) {
+      if (sn_lev[s] >= Lc) continue;
+      int r = s;
+      while (sn_par[r] >= 0 && sn_lev[sn_par[r]] < Lc) r = sn_par[r];
+      root[s] = r;
+      if (sub_of[r] < 0) sub_of[r] = nsub++;
+    }
+    bj->nsubtrees = nsub;
+    // bucket supernodes and panels by (subtree, level); inside a bucket: supernodes ascending, panels in panel order
+    std::vector<std::vector<int>> sn_b((size_t)nsub * Lc), fp_b((size_t)nsub * Lc), bp_b((size_t)nsub * Lc);
+    for (int s = 0; s < ns; ++s)
+      if (root[s] >= 0) sn_b[(size_t)sub_of[root[s]] * Lc + sn_lev[s]].push_back(s);
+    for (size_t i = 0; i < fp.size(); ++i) {
+      const int s = fp_sn[i];
+      if (root[s] >= 0) fp_b[(size_t)sub_of[root[s]] * Lc + sn_lev[s]].push_back((int)i);
+    }
+    for (size_t i = 0; i < bp.size(); ++i) {
+      const int s = bp_sn[i];
+      if (root[s] >= 0) bp_b[(size_t)sub_of[root[s]] * Lc + sn_lev[s]].push_back((int)i);
+    }
+    bot_lv.resize((size_t)nsub * Lc);
+    for (size_t k = 0; k < bot_lv.size(); ++k) {
+      BottomLevel& L = bot_lv[k];
+      L.c0 = (int)bot_cols.size();
+      for (int s : sn_b[k])
+        for (int c = 0; c < sn_w[s]; ++c) bot_cols.push_back(sn_c0[s] + c);
+      L.c1 = (int)bot_cols.size();
+      L.f0 = (int)bot_fp.size();
+      bot_fp.insert(bot_fp.end(), fp_b[k].begin(), fp_b[k].end());
+      L.f1 = (int)bot_fp.size();
+      L.b0 = (int)bot_bp.size();
+      bot_bp.insert(bot_bp.end(), bp_b[k].begin(), bp_b[k].end());
+      L.b1 = (int)bot_bp.size();
+    }
+  }
   bj->stat[7] = now_s() - t_an0;
 
   // ---------------------------------------------------------------- device buffers
@@ -696,6 +744,9 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   if (upload(&bj->fwd_panels, fp) || upload(&bj->bwd_panels, bp) || upload(&bj->fwd_units, fu) ||
       upload(&bj->bwd_units, bu) || upload(&bj->perm, perm) || upload(&bj->rows, rows) ||
       upload(&bj->lvl_cols, lvl_cols) || upload(&bj->gl_ptr, gl_ptr) || upload(&bj->gl_idx, gl_idx))
+    return 1;
+  if (bj->bottom > 0 && (upload(&bj->bot_lv, bot_lv) || upload(&bj->bot_cols, bot_cols) || upload(&bj->bot_fp, bot_fp) ||
+                         upload(&bj->bot_bp, bot_bp)))
     return 1;
 
   // ---------------------------------------------------------------- numeric factorisation

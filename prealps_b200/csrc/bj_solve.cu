@@ -482,6 +482,116 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
   store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
 }
 
+// ---- the bottom of the forest in one launch per direction (opt-in: PREALPS_BJ_BOTTOM=Lc when the factor is created;
+// written after the last GPU session of round 1 and checked on the CPU emulation only).  With one subdomain per GPU the
+// levels below Lc hold a few MB each and cost assemble + sweep + tiny-panel launches of pure latency.  Here a CTA owns a
+// whole subtree hanging below level Lc and walks it level by level: assemble the columns of its supernodes at that level,
+// __syncthreads, their panels (one warp each, straight from global memory: the panels are tiny), __syncthreads.  What a
+// column gathers comes from its descendants, all in the same subtree.  Everything the CTA wrote itself (Wk, U, Y, Xp)
+// is read back with ld.global.cg (L2), never through the non-coherent path.  Same operation order per panel and per
+// gather list as the level-by-level kernels.
+struct BottomArgs {
+  const BottomLevel* lv;
+  const int* cols;
+  const int* fp;
+  const int* bp;
+  int nlev;  // Lc
+  const double* B;
+  int ldb;
+  const long long* gl_ptr;
+  const long long* gl_idx;
+  const FwdPanel* fpan;
+  const BwdPanel* bpan;
+  const double* fdata;
+  const double* bdata;
+};
+
+template <int T, bool FWD>
+__device__ __forceinline__ void bottom_panel(const SweepArgs& a, const BottomArgs& b, int pidx, int lane) {
+  constexpr int NB = (T + 7) / 8;
+  const int lr = lane >> 2, lk = lane & 3;
+  long long off;
+  int klen, c0, w, h, row0;
+  long long uoff = 0, rows_off = 0;
+  if (FWD) {
+    const FwdPanel p = b.fpan[pidx];
+    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.row0; uoff = p.uoff;
+  } else {
+    const BwdPanel p = b.bpan[pidx];
+    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
+  }
+  const double* base = (FWD ? b.fdata : b.bdata) + off + lane * 4;
+  const int* rows = a.rows + rows_off;
+  double acc[4][NB][2];
+#pragma unroll
+  for (int rg = 0; rg < 4; ++rg)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
+  const int nkb = klen >> 2;
+  for (int kb = 0; kb < nkb; ++kb) {
+    double2 m0, m1;
+    ld_stream4(base + (size_t)kb * 128, m0, m1);
+    const int k = min(4 * kb + lk, klen - 1);  // steps past the panel are clamped: their panel entries are zero padding
+    const double* src;
+    if (FWD) src = a.Wk + (size_t)(c0 + k) * T;
+    else {
+      const int i = min(row0 + k, h - 1);
+      src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
+    }
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const double bf = (8 * nb + lr < T) ? __ldcg(src + 8 * nb + lr) : 0.0;
+      dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
+      dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
+      dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
+      dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+    }
+  }
+  store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
+}
+
+template <int T, bool FWD>
+__global__ void __launch_bounds__(kThreads) bottom_kernel(SweepArgs a, BottomArgs b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BottomLevel* lv = b.lv + (size_t)blockIdx.x * b.nlev;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (FWD) {
+    constexpr int CPL = (T >= 2) ? 2 : 1;
+    constexpr int G = T / CPL;
+    const int grp = threadIdx.x / G, lig = threadIdx.x % G;
+    const int cc = CPL * lig;
+    double* Wk = const_cast<double*>(a.Wk);
+    for (int l = 0; l < b.nlev; ++l) {
+      const BottomLevel L = lv[l];
+      for (int q = L.c0 + grp; q < L.c1; q += kThreads / G) {
+        const int c = b.cols[q];
+        const double* src = b.B + (size_t)a.perm[c] * b.ldb;
+        double a0 = 0.0, a1 = 0.0;
+        if (cc < a.t) a0 = src[cc];
+        if (CPL == 2 && cc + 1 < a.t) a1 = src[cc + 1];
+        const long long g1 = b.gl_ptr[c + 1];
+        for (long long g = b.gl_ptr[c]; g < g1; ++g) {  // list order = the order of assemble_kernel
+          const double* u = a.U + (size_t)b.gl_idx[g] * T + cc;
+          a0 -= __ldcg(u);
+          if (CPL == 2) a1 -= __ldcg(u + 1);
+        }
+        Wk[(size_t)c * T + cc] = a0;
+        if (CPL == 2) Wk[(size_t)c * T + cc + 1] = a1;
+      }
+      __syncthreads();
+      for (int p = L.f0 + warp; p < L.f1; p += kWarps) bottom_panel<T, true>(a, b, b.fp[p], lane);
+      __syncthreads();
+    }
+  } else {
+    for (int l = b.nlev - 1; l >= 0; --l) {
+      const BottomLevel L = lv[l];
+      for (int p = L.b0 + warp; p < L.b1; p += kWarps) bottom_panel<T, false>(a, b, b.bp[p], lane);
+      __syncthreads();
+    }
+  }
+}
+
 int pick_T(int t) { return t <= 1 ? 1 : t <= 2 ? 2 : t <= 4 ? 4 : t <= 8 ? 8 : t <= 16 ? 16 : 32; }
 
 int ensure_work(pcu_bj* bj, int T) {
@@ -606,7 +716,15 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   a.Wk = bj->Wk; a.Y = bj->Y; a.U = bj->U; a.Xp = bj->Xp; a.rows = bj->rows; a.perm = bj->perm;
   a.Out = X; a.ldo = ldx; a.t = t;
   a.scratch = bj->scratch; a.counters = bj->counters;
-  for (int l = 0; l < bj->nlevels; ++l) {
+  const int lbot = (bj->bottom > 0 && bj->nsubtrees > 0) ? bj->bottom : 0;  // levels [0, lbot): one launch per direction
+  BottomArgs ba{bj->bot_lv, bj->bot_cols, bj->bot_fp, bj->bot_bp, lbot, B, ldb, bj->gl_ptr, bj->gl_idx,
+                bj->fwd_panels, bj->bwd_panels, bj->fwd_data, bj->bwd_data};
+  if (lbot > 0) {
+    prof.mark("fwd bottom subtrees=" + std::to_string(bj->nsubtrees), 0.0);
+    launch_chain(bottom_kernel<T, true>, bj->nsubtrees, kThreads, 0, st, a, ba);
+    PCU_LAUNCH_CHECK(c);
+  }
+  for (int l = lbot; l < bj->nlevels; ++l) {
     const int ncols = bj->lvl_col_ptr[l + 1] - bj->lvl_col_ptr[l];
     if (ncols > 0) {
       prof.mark("asm L" + std::to_string(l) + " cols=" + std::to_string(ncols), 3.0 * ncols * T * 8);
@@ -637,7 +755,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       PCU_LAUNCH_CHECK(c);
     }
   }
-  for (int l = bj->nlevels - 1; l >= 0; --l) {
+  for (int l = bj->nlevels - 1; l >= lbot; --l) {
     const int nu = bj->bwd_unit_ptr[l + 1] - bj->bwd_unit_ptr[l];
     if (nu > 0) {
       prof.mark("bwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->bwd_lvl_bytes[l] - bj->bwd_tiny_bytes[l]);
@@ -655,6 +773,11 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       c->launches++;
       PCU_LAUNCH_CHECK(c);
     }
+  }
+  if (lbot > 0) {
+    prof.mark("bwd bottom subtrees=" + std::to_string(bj->nsubtrees), 0.0);
+    launch_chain(bottom_kernel<T, false>, bj->nsubtrees, kThreads, 0, st, a, ba);
+    PCU_LAUNCH_CHECK(c);
   }
   prof.report();
   return 0;

@@ -151,3 +151,36 @@ def test_graph_candidate_replays_the_same_chain(emul, monkeypatch):
         assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0
         assert np.array_equal(X4, base)
     lib.pcu_bj_destroy(bj)
+
+
+@pytest.mark.parametrize("nblk,t", [(2, 8), (1, 3)])
+def test_bottom_of_forest_candidate_is_bit_identical(emul, monkeypatch, nblk, t):
+    """PREALPS_BJ_BOTTOM=Lc: levels [0, Lc) as one forward and one backward launch, a CTA per subtree; same operation order
+    per panel and per gather list as the level-by-level kernels, far fewer launches"""
+    lib, ctx = emul
+    lib.emul_launch_count.restype = C.c_longlong
+    A = gen_matrices.poisson7(6).tocsr()
+    n = A.shape[0]
+    ld = t if t % 2 == 0 else t + 1
+    B = np.random.default_rng(t).standard_normal((n, ld))
+    out, launches = {}, {}
+    for Lc in (0, 2, 99):
+        if Lc:
+            monkeypatch.setenv("PREALPS_BJ_BOTTOM", str(Lc))
+        else:
+            monkeypatch.delenv("PREALPS_BJ_BOTTOM", raising=False)
+        rc, bj, cuts, blocks = factor(emul, A, nblk)
+        assert rc == 0, lib.pcu_last_error()
+        X = np.full((n, ld), np.nan)
+        l0 = lib.emul_launch_count(ctx)
+        assert lib.pcu_bj_apply(bj, dp(B), ld, dp(X), ld, t) == 0, lib.pcu_last_error()
+        launches[Lc] = lib.emul_launch_count(ctx) - l0
+        out[Lc] = X[:, :t].copy()
+        B2 = B.copy()  # in place
+        assert lib.pcu_bj_apply(bj, dp(B2), ld, dp(B2), ld, t) == 0
+        assert np.array_equal(B2[:, :t], out[Lc])
+        lib.pcu_bj_destroy(bj)
+    ref = direct(blocks, cuts, B[:, :t])
+    assert np.linalg.norm(out[0] - ref) <= 1e-12 * np.linalg.norm(ref)
+    assert np.array_equal(out[2], out[0]) and np.array_equal(out[99], out[0])
+    assert launches[99] == 2 and launches[99] < launches[2] < launches[0]

@@ -276,6 +276,46 @@ def test_block_jacobi_candidates_are_bit_identical(dev, t, var, monkeypatch):
     cu.pcu_bj_destroy(bj)
 
 
+@candidates
+@pytest.mark.parametrize("t", [1, 8, 16])
+def test_block_jacobi_bottom_candidate(dev, t, monkeypatch):
+    """PREALPS_BJ_BOTTOM=Lc (read when the factor is created): levels [0, Lc) as one launch per direction.  Same operation
+    order per panel and gather list: bit-identical on the CPU emulation; on the GPU the DMMA order inside a k-block is the
+    hardware's either way, so equality is expected too and 1e-13 is asserted"""
+    import scipy.sparse.linalg as spla
+    A = gen_matrices.poisson7(16).tocsr()
+    n = A.shape[0]
+    cuts = np.array([0, n // 2, n], dtype=np.int32)
+    blocks = [A[cuts[b]:cuts[b + 1], cuts[b]:cuts[b + 1]].tocsr() for b in range(2)]
+    keep = []
+    for Bk in blocks:
+        U = sp.triu(Bk, format="csr")
+        U.sort_indices()
+        keep.append((U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data.copy()))
+    rp = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[0]) for k in keep])
+    ci = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[1]) for k in keep])
+    vv = (C.POINTER(C.c_double) * 2)(*[capi.dp(k[2]) for k in keep])
+    B = np.random.default_rng(t).standard_normal((n, t))
+    ref = np.vstack([spla.splu(Bk.tocsc()).solve(B[cuts[b]:cuts[b + 1]]) for b, Bk in enumerate(blocks)])
+    out = {}
+    for Lc in (0, 3, 6, 99):
+        if Lc:
+            monkeypatch.setenv("PREALPS_BJ_BOTTOM", str(Lc))
+        else:
+            monkeypatch.delenv("PREALPS_BJ_BOTTOM", raising=False)
+        bj = C.c_void_p()
+        assert cu.pcu_bj_create(dev.ctx, 2, capi.ip(cuts), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
+        dB, dX = dev.up(B), dev.zeros(n * t)
+        for rep in range(3):
+            assert cu.pcu_bj_apply(bj, dB, t, dX, t, t) == 0, cu.pcu_last_error()
+        out[Lc] = dev.down(dX, (n, t))
+        assert np.linalg.norm(out[Lc] - ref) < 1e-11 * np.linalg.norm(ref)
+        dev.free(dB, dX)
+        cu.pcu_bj_destroy(bj)
+    for Lc in (3, 6, 99):
+        assert np.abs(out[Lc] - out[0]).max() <= 1e-13 * np.abs(out[0]).max()
+
+
 def test_block_jacobi_long_panels_cut_across_ctas(dev):
     """a block large enough for separators beyond 1024 columns: exercises the inter-CTA split of long panels"""
     import scipy.sparse.linalg as spla
