@@ -506,8 +506,13 @@ struct BottomArgs {
   const double* bdata;
 };
 
+constexpr int kBotK = 32;  // k steps staged per round by a warp of bottom_kernel (the landing buffer of sweep_tiny_kernel)
+
+// one panel by one warp, kBotK steps at a time: the slice of the panel and its input rows are copied to the warp's
+// shared-memory buffer with cp.async in one go (one memory round trip per 32 steps instead of one per k-block)
 template <int T, bool FWD>
-__device__ __forceinline__ void bottom_panel(const SweepArgs& a, const BottomArgs& b, int pidx, int lane) {
+__device__ __forceinline__ void bottom_panel(const SweepArgs& a, const BottomArgs& b, int pidx, int lane, double* mbuf,
+                                             double* bbuf) {
   constexpr int NB = (T + 7) / 8;
   const int lr = lane >> 2, lk = lane & 3;
   long long off;
@@ -522,37 +527,68 @@ __device__ __forceinline__ void bottom_panel(const SweepArgs& a, const BottomArg
   }
   const double* base = (FWD ? b.fdata : b.bdata) + off + lane * 4;
   const int* rows = a.rows + rows_off;
+  const unsigned long long pol = l2_evict_first_policy();
   double acc[4][NB][2];
 #pragma unroll
   for (int rg = 0; rg < 4; ++rg)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
-  const int nkb = klen >> 2;
-  for (int kb = 0; kb < nkb; ++kb) {
-    double2 m0, m1;
-    ld_stream4(base + (size_t)kb * 128, m0, m1);
-    const int k = min(4 * kb + lk, klen - 1);  // steps past the panel are clamped: their panel entries are zero padding
-    const double* src;
-    if (FWD) src = a.Wk + (size_t)(c0 + k) * T;
-    else {
-      const int i = min(row0 + k, h - 1);
-      src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
+  for (int k0 = 0; k0 < klen; k0 += kBotK) {
+    const int nk = min(kBotK, klen - k0);  // a multiple of 4
+    const int nkb = nk >> 2;
+    for (int kb = 0; kb < nkb; ++kb) {
+      cp_async16_stream(mbuf + kb * 128 + lane * 4, base + (size_t)(k0 / 4 + kb) * 128, pol);
+      cp_async16_stream(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)(k0 / 4 + kb) * 128 + 2, pol);
     }
+    if (T >= 2) {
+      constexpr int CPR = (T >= 2) ? T / 2 : 1;
+      for (int qq = lane; qq < nk * CPR; qq += 32) {
+        const int r = qq / CPR, part = qq % CPR;
+        const int k = min(k0 + r, klen - 1);  // steps past the panel are clamped: their panel entries are zero padding
+        const double* src;
+        if (FWD) src = a.Wk + (size_t)(c0 + k) * T;
+        else {
+          const int i = min(row0 + k, h - 1);
+          src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
+        }
+        cp_async16(bbuf + (size_t)r * T + 2 * part, src + 2 * part);
+      }
+    } else {
+      for (int r = lane; r < nk; r += 32) {
+        const int k = min(k0 + r, klen - 1);
+        const double* src;
+        if (FWD) src = a.Wk + (size_t)(c0 + k);
+        else { const int i = min(row0 + k, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
+        bbuf[r] = __ldcg(src);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int kb = 0; kb < nkb; ++kb) {
+      const double2 m0 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4);
+      const double2 m1 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4 + 2);
+      const double* brow = bbuf + (size_t)(4 * kb + lk) * T;
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const double bf = (8 * nb + lr < T) ? __ldcg(src + 8 * nb + lr) : 0.0;
-      dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
-      dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
-      dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
-      dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+      for (int nb = 0; nb < NB; ++nb) {
+        const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
+        dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
+        dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
+        dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
+        dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+      }
     }
+    __syncwarp();  // the buffers are refilled by the next round
   }
   store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
 }
 
 template <int T, bool FWD>
 __global__ void __launch_bounds__(kThreads) bottom_kernel(SweepArgs a, BottomArgs b) {
+  PCU_DYN_SMEM(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* mbuf = smem + (size_t)warp * (kBotK * 32 + kBotK * T);  // warp-private: kBotK steps of panel data ...
+  double* bbuf = mbuf + kBotK * 32;                               // ... and of T-wide input rows
   const BottomLevel* lv = b.lv + (size_t)blockIdx.x * b.nlev;
   pdl_wait();
   pdl_launch_dependents();
@@ -580,13 +616,13 @@ __global__ void __launch_bounds__(kThreads) bottom_kernel(SweepArgs a, BottomArg
         if (CPL == 2) Wk[(size_t)c * T + cc + 1] = a1;
       }
       __syncthreads();
-      for (int p = L.f0 + warp; p < L.f1; p += kWarps) bottom_panel<T, true>(a, b, b.fp[p], lane);
+      for (int p = L.f0 + warp; p < L.f1; p += kWarps) bottom_panel<T, true>(a, b, b.fp[p], lane, mbuf, bbuf);
       __syncthreads();
     }
   } else {
     for (int l = b.nlev - 1; l >= 0; --l) {
       const BottomLevel L = lv[l];
-      for (int p = L.b0 + warp; p < L.b1; p += kWarps) bottom_panel<T, false>(a, b, b.bp[p], lane);
+      for (int p = L.b0 + warp; p < L.b1; p += kWarps) bottom_panel<T, false>(a, b, b.bp[p], lane, mbuf, bbuf);
       __syncthreads();
     }
   }
@@ -660,6 +696,17 @@ void launch_tiny_one(int first, int count, cudaStream_t st, const SweepArgs& a) 
   launch_chain(sweep_tiny_kernel<T, FWD, KMAX, WARPS>, (count + WARPS - 1) / WARPS, WARPS * 32, bytes, st, a, first, count);
 }
 
+template <int T, bool FWD>
+void launch_bottom(int nsub, cudaStream_t st, const SweepArgs& a, const BottomArgs& b) {
+  constexpr int bytes = kWarps * (kBotK * 32 + kBotK * T) * (int)sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(bottom_kernel<T, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    configured = true;
+  }
+  launch_chain(bottom_kernel<T, FWD>, nsub, kThreads, bytes, st, a, b);
+}
+
 // panels [first, first + count) are sorted by length, the last `nshort` ones have klen <= kTinyS: each class gets a
 // landing buffer of its own size (more resident warps for the shorter panels)
 template <int T, bool FWD>
@@ -721,7 +768,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
                 bj->fwd_panels, bj->bwd_panels, bj->fwd_data, bj->bwd_data};
   if (lbot > 0) {
     prof.mark("fwd bottom subtrees=" + std::to_string(bj->nsubtrees), 0.0);
-    launch_chain(bottom_kernel<T, true>, bj->nsubtrees, kThreads, 0, st, a, ba);
+    launch_bottom<T, true>(bj->nsubtrees, st, a, ba);
     PCU_LAUNCH_CHECK(c);
   }
   for (int l = lbot; l < bj->nlevels; ++l) {
@@ -776,7 +823,7 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   }
   if (lbot > 0) {
     prof.mark("bwd bottom subtrees=" + std::to_string(bj->nsubtrees), 0.0);
-    launch_chain(bottom_kernel<T, false>, bj->nsubtrees, kThreads, 0, st, a, ba);
+    launch_bottom<T, false>(bj->nsubtrees, st, a, ba);
     PCU_LAUNCH_CHECK(c);
   }
   prof.report();
