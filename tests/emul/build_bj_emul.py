@@ -38,9 +38,11 @@ def rewrite_launches(text):
     return out, n
 
 
-def build():
+def build(asan=False):
+    """asan=True: the same library under AddressSanitizer (load it with LD_PRELOAD=libasan): out-of-bounds accesses of the
+    kernels to "device" memory, which is host memory with red zones here"""
     os.makedirs(BUILD, exist_ok=True)
-    so = os.path.join(BUILD, "libbj_emul.so")
+    so = os.path.join(BUILD, "libbj_emul_asan.so" if asan else "libbj_emul.so")
     deps = [os.path.join(CSRC, f) for f in ("bj_factor.cu", "bj_solve.cu", "bj_symbolic.cpp", "bj.h", "bj_symbolic.h", "common.cuh")]
     deps += [os.path.join(EMUL, f) for f in ("cuda_emul.h", "cuda_emul.cpp", "bj_emul_glue.cpp", "build_bj_emul.py")]
     if os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
@@ -51,7 +53,8 @@ def build():
     open(gen, "w").write('#define PCU_EMUL 1\n#line 1 "bj_factor.cu"\n' + text)
     gen2 = os.path.join(BUILD, "bj_solve_emul.cpp")
     open(gen2, "w").write('#define PCU_EMUL 1\n#include "%s"\n' % os.path.join(CSRC, "bj_solve.cu"))
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I" + EMUL, "-I" + CSRC,
+    extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    cmd = ["g++", "-O1"] + extra + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I" + EMUL, "-I" + CSRC,
            gen, gen2, os.path.join(CSRC, "bj_symbolic.cpp"), os.path.join(EMUL, "cuda_emul.cpp"),
            os.path.join(EMUL, "bj_emul_glue.cpp"), METIS_A, "-o", so, "-lm", "-Wl,-Bsymbolic", "-Wl,--exclude-libs=ALL"]  # own symbols first: the product library may be loaded RTLD_GLOBAL
     subprocess.check_call(cmd)

@@ -184,3 +184,16 @@ def test_bottom_of_forest_candidate_is_bit_identical(emul, monkeypatch, nblk, t)
     assert np.linalg.norm(out[0] - ref) <= 1e-12 * np.linalg.norm(ref)
     assert np.array_equal(out[2], out[0]) and np.array_equal(out[99], out[0])
     assert launches[99] == 2 and launches[99] < launches[2] < launches[0]
+
+
+def test_kernels_under_address_sanitizer():
+    """the same emulation built with -fsanitize=address: "device" buffers are host allocations with red zones, so an
+    out-of-bounds access of a kernel (factorisation, sweeps, bottom-of-the-forest launch) aborts the run"""
+    import subprocess
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan is not available")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "bj_asan_case.py")], env=env, capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0 and "asan case ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
