@@ -5,7 +5,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.join(_HERE, "lib")
+# PREALPS_B200_LIBDIR: tests/emul loads the CPU emulation of the CUDA kernels (tests/_build/emul_lib) through the same binding;
+# the product libraries live in prealps_b200/lib and have no CPU path
+LIBDIR = os.environ.get("PREALPS_B200_LIBDIR") or os.path.join(_HERE, "lib")
 
 
 def _load(name):

@@ -424,10 +424,23 @@ __global__ void __launch_bounds__(kThreads) update_z_v2_kernel(int m, double* Z,
 // so the products need NO shuffles and NO shared-memory reads in the loop (the CUDA-core versions above are
 // bound by exactly those: ncu showed l1tex at 50-80 % with DRAM at 44-52 %), and only 2 accumulator doubles per
 // lane and 8x8 block, which leaves the registers for loads in flight.
+#ifndef PCU_EMUL
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+#else  // tests/emul: the same product as a warp-wide exchange (lane holds A[lane/4][lane%4], B[lane%4][lane/4], D[lane/4][2*(lane%4)+{0,1}])
+inline void dmma884(double& d0, double& d1, double a, double b) {
+  double A[32], B[32];
+  emul_warp_allgather(a, A);
+  emul_warp_allgather(b, B);
+  const int lane = (int)(threadIdx.x & 31), row = lane >> 2, n0 = 2 * (lane & 3);
+  for (int k = 0; k < 4; ++k) {
+    d0 = fma(A[row * 4 + k], B[n0 * 4 + k], d0);
+    d1 = fma(A[row * 4 + k], B[(n0 + 1) * 4 + k], d1);
+  }
+}
+#endif
 
 template <int T>
 __global__ void __launch_bounds__(kThreads) gram2_mma_kernel(int m, const double* __restrict__ A1, int lda1,

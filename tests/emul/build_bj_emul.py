@@ -28,14 +28,47 @@ def split_top(s):
 
 
 def rewrite_launches(text):
-    pat = re.compile(r"(\b\w+)<<<(.*?)>>>\((.*?)\);", re.S)
-
-    def sub(m):
-        cfg = split_top(m.group(2))
-        assert len(cfg) == 4, cfg
-        return "emul_launch(%s, %s, %s, [&] { %s(%s); });" % (cfg[0], cfg[1], cfg[2], m.group(1), m.group(3))
-    out, n = pat.subn(sub, text)
-    return out, n
+    """every `name<targs><<<grid, block, smem, stream>>>(args)` becomes `emul_launch(grid, block, smem, [&] { name<targs>(args); })`
+    (an expression: it also works inside macro bodies and macro arguments)"""
+    out, pos, n = "", 0, 0
+    while True:
+        i = text.find("<<<", pos)
+        if i < 0:
+            return out + text[pos:], n
+        # kernel name: identifier, optionally followed by balanced template arguments
+        j = i
+        if text[j - 1] == ">":
+            depth = 0
+            while True:
+                j -= 1
+                if text[j] == ">":
+                    depth += 1
+                elif text[j] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+        k = j
+        while k > 0 and (text[k - 1].isalnum() or text[k - 1] in "_:"):
+            k -= 1
+        name = text[k:i]
+        e = text.find(">>>", i)
+        cfg = split_top(text[i + 3:e])
+        assert len(cfg) == 4, (name, cfg)
+        a0 = e + 3
+        assert text[a0] == "(", text[a0:a0 + 20]
+        depth, a1 = 0, a0
+        while True:
+            if text[a1] == "(":
+                depth += 1
+            elif text[a1] == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            a1 += 1
+        args = text[a0 + 1:a1]
+        out += text[pos:k] + "emul_launch(%s, %s, %s, [&] { %s(%s); })" % (cfg[0], cfg[1], cfg[2], name, args)
+        pos = a1 + 1
+        n += 1
 
 
 def build(asan=False):
@@ -63,3 +96,37 @@ def build(asan=False):
 
 if __name__ == "__main__":
     print(build())
+
+
+def build_full():
+    """the whole product stack for the emulation: every .cu of libprealps_cuda and the plain-C host layer, as
+    tests/_build/emul_lib/{libprealps_cuda,libprealps_b200,libmpishim}.so (same names: the host library finds the emulated
+    CUDA library next to itself).  Loaded only by tests (prealps_b200.capi honours PREALPS_B200_LIBDIR)."""
+    out = os.path.join(BUILD, "emul_lib")
+    os.makedirs(out, exist_ok=True)
+    cu = ["ctx.cu", "spmm.cu", "ecg_kernels.cu", "bj_factor.cu", "bj_solve.cu"]
+    host = [os.path.join(ROOT, "prealps_b200", "host", f) for f in ("pa_csr.c", "pa_operator.c", "pa_block_jacobi.c", "pa_ecg.c", "pa_driver.c")]
+    deps = [os.path.join(CSRC, f) for f in cu + ["bj_symbolic.cpp", "bj.h", "bj_symbolic.h", "common.cuh", "spmm_kernels.cuh"]] + host
+    deps += [os.path.join(EMUL, f) for f in ("cuda_emul.h", "cuda_emul.cpp", "build_bj_emul.py")]
+    deps += [os.path.join(ROOT, "mpishim", "mpishim.c")]
+    so_cuda, so_host, so_mpi = (os.path.join(out, n) for n in ("libprealps_cuda.so", "libprealps_b200.so", "libmpishim.so"))
+    if all(os.path.exists(x) for x in (so_cuda, so_host, so_mpi)) and all(os.path.getmtime(d) <= os.path.getmtime(so_host) for d in deps):
+        return out
+    gens = []
+    for f in cu:
+        text, _ = rewrite_launches(open(os.path.join(CSRC, f)).read())
+        assert "<<<" not in text
+        g = os.path.join(out, f.replace(".cu", "_emul.cpp"))
+        open(g, "w").write('#define PCU_EMUL 1\n#line 1 "%s"\n' % f + text)
+        gens.append(g)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I" + EMUL, "-I" + CSRC,
+                           "-I" + os.path.join(ROOT, "include")] + gens +
+                          [os.path.join(CSRC, "bj_symbolic.cpp"), os.path.join(EMUL, "cuda_emul.cpp"), METIS_A, "-o", so_cuda, "-lm", "-ldl",
+                           "-Wl,-Bsymbolic", "-Wl,--exclude-libs=ALL"])
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=gnu99", "-shared", "-Wno-unused-result", "-I" + os.path.join(ROOT, "mpishim"),
+                           os.path.join(ROOT, "mpishim", "mpishim.c"), "-o", so_mpi, "-lpthread"])
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=gnu99", "-shared", "-Wno-unused-result", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(ROOT, "mpishim")] + host +
+                          [METIS_A, "-Wl,--exclude-libs=ALL", "-L" + out, "-lprealps_cuda", "-lmpishim", "-Wl,-rpath,$ORIGIN", "-o", so_host,
+                           "-lm", "-lpthread"])
+    return out

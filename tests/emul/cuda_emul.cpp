@@ -18,6 +18,19 @@ cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) {
   return *g ? cudaSuccess : 1;
 }
 
+#include <map>
+static std::mutex g_reg_mutex;
+static std::map<uintptr_t, size_t> g_reg;
+void emul_register(const void* p, size_t bytes) { std::lock_guard<std::mutex> lk(g_reg_mutex); g_reg[(uintptr_t)p] = bytes; }
+void emul_unregister(const void* p) { std::lock_guard<std::mutex> lk(g_reg_mutex); g_reg.erase((uintptr_t)p); }
+bool emul_is_device(const void* p) {
+  std::lock_guard<std::mutex> lk(g_reg_mutex);
+  auto it = g_reg.upper_bound((uintptr_t)p);
+  if (it == g_reg.begin()) return false;
+  --it;
+  return (uintptr_t)p < it->first + it->second;
+}
+
 namespace {
 
 // barrier whose participants may leave for good (a CUDA thread that returns stops counting)

@@ -68,6 +68,19 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src_lane) {
   return (T)all[src_lane & 31];
 }
 
+template <class T> inline T __shfl_sync(unsigned, T v, int src_lane, int width) {  // sub-warp segments of `width` lanes
+  double all[32];
+  emul_warp_allgather((double)v, all);
+  const int lane = (int)(threadIdx.x & 31), base = lane / width * width;
+  return (T)all[base + (src_lane % width)];
+}
+template <class T> inline T __shfl_down_sync(unsigned, T v, int delta) {
+  double all[32];
+  emul_warp_allgather((double)v, all);
+  const int lane = (int)(threadIdx.x & 31);
+  return (lane + delta < 32) ? (T)all[lane + delta] : v;
+}
+
 inline void pcu_emul_check_aligned(const void* p, size_t a) {
   if (reinterpret_cast<uintptr_t>(p) % a != 0) {
     std::fprintf(stderr, "[emul] misaligned %zu-byte vector access at %p\n", a, p);
@@ -96,6 +109,24 @@ struct cudaLaunchConfig_t {
   unsigned numAttrs = 0;
 };
 
+void emul_register(const void* p, size_t bytes);   // "device" allocations, for cudaPointerGetAttributes
+void emul_unregister(const void* p);
+bool emul_is_device(const void* p);
+struct cudaDeviceProp { int multiProcessorCount; };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; };
+typedef void* cudaMemPool_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaMemPoolAttrReleaseThreshold = 4 };
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 4; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+  a->type = emul_is_device(p) ? cudaMemoryTypeDevice : cudaMemoryTypeUnregistered;
+  return cudaSuccess;
+}
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
@@ -103,10 +134,23 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
   void* q = nullptr;
   if (posix_memalign(&q, 256, bytes ? bytes : 256) != 0) return 2;
   std::memset(q, 0xEE, bytes ? bytes : 256);  // fresh device memory is garbage
+  emul_register(q, bytes ? bytes : 256);
   *p = static_cast<T*>(q);
   return cudaSuccess;
 }
-inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) { if (p) emul_unregister(p); std::free(p); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
+inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
+template <class T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { *p = static_cast<T*>(std::malloc(bytes ? bytes : 8)); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr) {
+  for (size_t i = 0; i < h; ++i) std::memcpy(static_cast<char*>(d) + i * dp, static_cast<const char*>(s) + i * sp, w);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMemset2DAsync(void* d, size_t dp, int v, size_t w, size_t h, cudaStream_t = nullptr) {
+  for (size_t i = 0; i < h; ++i) std::memset(static_cast<char*>(d) + i * dp, v, w);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }
@@ -115,6 +159,8 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 inline double emul_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emul_event{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = emul_now(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

@@ -1,0 +1,57 @@
+"""The whole stack on the CPU emulation (tests/emul): the plain-C host layer (libprealps_b200) on top of every CUDA kernel of
+libprealps_cuda compiled against a miniature CUDA runtime -- operator build, block-Jacobi factorisation, ECG iterations --
+against a golden run of the reference and against the numpy restatement, and the opt-in kernel candidates against the
+default kernels bit for bit over a whole solve.  TEST INFRASTRUCTURE: logic and data flow only; the product libraries
+have no CPU path and the -m gpu tests remain the parity tests proper."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import gen_matrices
+import restate
+from conftest import GOLDEN, ROOT
+
+CASE = os.path.join(ROOT, "tests", "emul", "full_solve_case.py")
+CANDIDATE_VARS = ("PREALPS_SPMM_LEAN", "PREALPS_SPMM_BULK", "PREALPS_BJ_BOTTOM", "PREALPS_BJ_GRAPH", "PREALPS_BJ_ASM_PREFETCH",
+                  "PREALPS_SPMM_OVERLAP")
+
+
+def solve(spec, **switches):
+    env = {k: v for k, v in os.environ.items() if k not in CANDIDATE_VARS and k != "PREALPS_B200_LIBDIR"}
+    env.update(switches)
+    out = subprocess.run([sys.executable, CASE, spec], env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    r["hist"] = np.array([float.fromhex(x) for x in r["hist"]])
+    return r
+
+
+def test_golden_case_on_the_emulated_stack():
+    name = "poisson7_n8_s4_t4_odir"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    r = solve(name)
+    assert r["iter"] == int(g["iter"])
+    n = min(len(r["hist"]), len(g["res_hist"]))
+    assert np.allclose(r["hist"][:n], g["res_hist"][:n], rtol=1e-6)
+    assert r["true_relres"] < 10 * float(g["tol"])
+
+
+def test_candidates_over_a_whole_solve():
+    """t = 8 so that the SpMM candidates engage; every candidate keeps the operation order of the kernel it replaces, so
+    the residual history of the whole solve is the same bits"""
+    spec = "poisson7:8:8:8:1e-8"
+    base = solve(spec)
+    P = restate.Partitioned(gen_matrices.poisson7(8).tocsr(), 8)
+    ref = restate.ecg_solve(P, 8, 1e-8)
+    assert abs(base["iter"] - ref["iter"]) <= 1
+    n = min(len(base["hist"]), len(ref["res_hist"]))
+    assert np.allclose(base["hist"][:n], ref["res_hist"][:n], rtol=1e-6)
+    a = solve(spec, PREALPS_SPMM_LEAN="1", PREALPS_BJ_BOTTOM="2", PREALPS_BJ_GRAPH="1", PREALPS_BJ_ASM_PREFETCH="1")
+    b = solve(spec, PREALPS_SPMM_BULK="1", PREALPS_BJ_BOTTOM="99")
+    for r in (a, b):
+        assert r["iter"] == base["iter"] and np.array_equal(r["hist"], base["hist"]) and r["sol_sum"] == base["sol_sum"]
+        assert r["launches"] < base["launches"]
