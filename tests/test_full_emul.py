@@ -55,3 +55,28 @@ def test_candidates_over_a_whole_solve():
     for r in (a, b):
         assert r["iter"] == base["iter"] and np.array_equal(r["hist"], base["hist"]) and r["sol_sum"] == base["sol_sum"]
         assert r["launches"] < base["launches"]
+
+
+def test_unchanged_reference_driver_on_the_emulated_stack(tmp_path):
+    """examples/test_ecg_prealps_op.c of the reference, compiled unchanged (prealps_b200/bin), one process per subdomain over
+    the MPI shim, with the emulated libraries in front of its RUNPATH: the multi-process path (halo plan, pack kernel,
+    boundary rows through host MPI, all-reduces) against the reference's golden run"""
+    exe = os.path.join(ROOT, "prealps_b200", "bin", "test_ecg_prealps_op")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built (reference tree was absent at build time)")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    import build_bj_emul
+    libdir = build_bj_emul.build_full()
+    name = "poisson7_n8_s4_t4_odir"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    mtx = str(tmp_path / "A.mtx")
+    gen_matrices.write_mtx(mtx, gen_matrices.build(g["gen"], g["N"]))
+    env = {k: v for k, v in os.environ.items() if k not in CANDIDATE_VARS}
+    env.update(LD_LIBRARY_PATH=libdir, MPISHIM_NP=str(int(g["S"])))
+    out = subprocess.run([exe, "-e", str(int(g["t"])), "-m", mtx, "-o", str(int(g["ortho"])), "-r", "0", "-t", repr(float(g["tol"]))],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    it = int([l for l in out.stdout.splitlines() if "iter:" in l][0].split(":")[1])
+    res = float([l for l in out.stdout.splitlines() if "res :" in l][0].split(":")[1])
+    assert it == int(g["iter"])
+    assert res == pytest.approx(float(g["res"]), rel=1e-5)
