@@ -86,7 +86,8 @@ def build(asan=False):
     open(gen, "w").write('#define PCU_EMUL 1\n#line 1 "bj_factor.cu"\n' + text)
     gen2 = os.path.join(BUILD, "bj_solve_emul.cpp")
     open(gen2, "w").write('#define PCU_EMUL 1\n#include "%s"\n' % os.path.join(CSRC, "bj_solve.cu"))
-    extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    # the sanitizer build keeps one OS thread per CUDA thread (EMUL_PTHREADS); the default engine schedules fibers
+    extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-DEMUL_PTHREADS"] if asan else []
     cmd = ["g++", "-O1"] + extra + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I" + EMUL, "-I" + CSRC,
            gen, gen2, os.path.join(CSRC, "bj_symbolic.cpp"), os.path.join(EMUL, "cuda_emul.cpp"),
            os.path.join(EMUL, "bj_emul_glue.cpp"), METIS_A, "-o", so, "-lm", "-Wl,-Bsymbolic", "-Wl,--exclude-libs=ALL"]  # own symbols first: the product library may be loaded RTLD_GLOBAL
