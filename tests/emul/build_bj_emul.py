@@ -96,7 +96,8 @@ def build(asan=False):
 
 
 if __name__ == "__main__":
-    print(build())
+    import sys
+    print(build_full() if "--full" in sys.argv else build(asan="--asan" in sys.argv))
 
 
 def build_full():
