@@ -70,3 +70,15 @@ def test_unchanged_reference_driver_on_the_emulated_stack(tmp_path):
     res = float([l for l in out.stdout.splitlines() if "res :" in l][0].split(":")[1])
     assert it == int(g["iter"])
     assert res == pytest.approx(float(g["res"]), rel=1e-5)
+
+
+def test_bench_entry_points_on_the_emulated_stack():
+    """what bench.py calls underneath (it cannot run here itself: it needs torch.cuda for the clocks and the barriers)"""
+    env = {k: v for k, v in os.environ.items() if k not in CANDIDATE_VARS and k != "PREALPS_B200_LIBDIR"}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "bench_entry_case.py")], env=env, capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["M"] == 512 and r["launches"] > 0 and all(x > 0 for x in r["kernel_ms"])
+    assert r["true_relres"] < 1e-7 and 5 < r["iter"] < 40
+    assert r["spmm_bytes"] == 3200 * 12 + 513 * 4 + 2 * 512 * 8 * 8 and r["bj_bytes"] > 0  # SURVEY.md 8(d); 7-point 8^3: nnz = 7*512 - 6*64
