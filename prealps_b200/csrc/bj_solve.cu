@@ -606,11 +606,24 @@ __global__ void __launch_bounds__(kThreads) bottom_kernel(SweepArgs a, BottomArg
         double a0 = 0.0, a1 = 0.0;
         if (cc < a.t) a0 = src[cc];
         if (CPL == 2 && cc + 1 < a.t) a1 = src[cc + 1];
+        // the list is walked in order (the order of assemble_kernel); 8 slots are fetched at a time so the loads overlap
         const long long g1 = b.gl_ptr[c + 1];
-        for (long long g = b.gl_ptr[c]; g < g1; ++g) {  // list order = the order of assemble_kernel
-          const double* u = a.U + (size_t)b.gl_idx[g] * T + cc;
-          a0 -= __ldcg(u);
-          if (CPL == 2) a1 -= __ldcg(u + 1);
+        for (long long g = b.gl_ptr[c]; g < g1; g += 8) {
+          long long idx[8];
+          double v0[8], v1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) idx[j] = (g + j < g1) ? __ldg(b.gl_idx + g + j) : -1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v0[j] = v1[j] = 0.0;
+            if (idx[j] >= 0) {
+              const double* u = a.U + (size_t)idx[j] * T + cc;
+              v0[j] = __ldcg(u);
+              if (CPL == 2) v1[j] = __ldcg(u + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a0 -= v0[j]; a1 -= v1[j]; }
         }
         Wk[(size_t)c * T + cc] = a0;
         if (CPL == 2) Wk[(size_t)c * T + cc + 1] = a1;
