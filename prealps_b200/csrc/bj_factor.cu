@@ -376,6 +376,8 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   SymbolicOptions opt;
   if (const char* e = getenv("PREALPS_BJ_LEAF")) opt.leaf_cols = atoi(e);
   if (const char* e = getenv("PREALPS_BJ_RELAX")) opt.relax_zero = atof(e);
+  if (const char* e = getenv("PREALPS_BJ_RELAX_BIG")) opt.relax_big = atof(e);
+  if (const char* e = getenv("PREALPS_BJ_RELAX_BIG_COLS")) opt.relax_big_cols = atoi(e);
   {
     unsigned hw = std::thread::hardware_concurrency();
     int nthr = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)nblk);
@@ -890,6 +892,8 @@ int pcu_bj_analyze(int n, const int* rowPtr, const int* colInd, int use_metis, i
   opt.use_metis = use_metis != 0;
   if (const char* e = getenv("PREALPS_BJ_LEAF")) opt.leaf_cols = atoi(e);
   if (const char* e = getenv("PREALPS_BJ_RELAX")) opt.relax_zero = atof(e);
+  if (const char* e = getenv("PREALPS_BJ_RELAX_BIG")) opt.relax_big = atof(e);
+  if (const char* e = getenv("PREALPS_BJ_RELAX_BIG_COLS")) opt.relax_big_cols = atoi(e);
   const int rc = analyze(n, rowPtr, colInd, opt, &S);
   if (rc) return rc;
   if ((long long)S.sn_rows.size() > rows_cap) return -9;

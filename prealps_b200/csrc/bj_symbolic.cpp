@@ -258,7 +258,8 @@ int analyze(int n, const int* rowPtr, const int* colInd, const SymbolicOptions& 
       bool merge;
       if (wn <= opt.relax_small) merge = true;
       else if (wn <= 4 * opt.relax_small) merge = (double)zt < 1.5 * opt.relax_zero * (double)stor;
-      else merge = (double)zt < opt.relax_zero * (double)stor;
+      else if (wn <= opt.relax_big_cols) merge = (double)zt < opt.relax_zero * (double)stor;
+      else merge = (double)zt < opt.relax_big * (double)stor;
       if (!merge) break;
       p.first = c.first;
       p.h = hn;

@@ -35,6 +35,8 @@ struct SymbolicOptions {
   int leaf_cols = 32;       // merge a whole elimination subtree into one dense supernode if it has <= this many columns
   double relax_zero = 0.2;  // merge a last child into its parent if the fraction of explicit zeros stays below this
   int relax_small = 16;     // ... or if both are narrower than this
+  int relax_big_cols = 1 << 30;  // merged supernodes wider than this are held to relax_big instead: a wide supernode streams
+  double relax_big = 0.2;        // at full rate anyway, its explicit zeros are pure extra traffic
   bool use_metis = true;    // false: natural ordering (tests)
 };
 
