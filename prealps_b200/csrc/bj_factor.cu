@@ -354,12 +354,10 @@ int pcu_bj_destroy(pcu_bj* bj) {
   if (!bj) return 0;
   cudaSetDevice(bj->ctx->device);
   cudaStreamSynchronize(bj->ctx->stream);
-  for (auto& g : bj->graphs)
-    if (g.exec) cudaGraphExecDestroy(g.exec);
   cudaFree(bj->fwd_data); cudaFree(bj->bwd_data); cudaFree(bj->fwd_panels); cudaFree(bj->bwd_panels);
   cudaFree(bj->fwd_units); cudaFree(bj->bwd_units); cudaFree(bj->perm); cudaFree(bj->rows);
   cudaFree(bj->lvl_cols); cudaFree(bj->gl_ptr); cudaFree(bj->gl_idx);
-  cudaFree(bj->bot_lv); cudaFree(bj->bot_cols); cudaFree(bj->bot_fp); cudaFree(bj->bot_bp);
+  cudaFree(bj->all_units); cudaFree(bj->asm_tasks); cudaFree(bj->dep);
   cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp); cudaFree(bj->scratch); cudaFree(bj->counters);
   delete bj;
   return 0;
@@ -615,7 +613,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     std::vector<int> kl;
     for (auto& e : lst) {
       const int s = e.second.first, p = e.second.second;
-      FwdPanel P{fdoubles, uoff[s], e.first, sn_c0[s], 32 * p, sn_w[s], sn_h[s], 0};
+      FwdPanel P{fdoubles, uoff[s], e.first, sn_c0[s], 32 * p, sn_w[s], sn_h[s], -1, 0, -1, 0, 0};  // dependencies: below
       pk_f[l].push_back({zoff[s], fdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
       fdoubles += (long long)e.first * 32;
       bj->fwd_lvl_bytes[l] += 8.0 * e.first * 32;
@@ -641,7 +639,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     const int b0 = (int)bp.size();
     for (auto& e : lst) {
       const int s = e.second.first, p = e.second.second;
-      BwdPanel P{bdoubles, sn_rp[s], e.first, 32 * p, sn_c0[s], sn_w[s], sn_h[s], 0};
+      BwdPanel P{bdoubles, sn_rp[s], e.first, 32 * p, sn_c0[s], sn_w[s], sn_h[s], -1, 0, -1, 0, 0};
       pk_b[l].push_back({zoff[s], bdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
       bdoubles += (long long)e.first * 32;
       bj->bwd_lvl_bytes[l] += 8.0 * e.first * 32;
@@ -676,49 +674,87 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     for (int s = 0; s < ns; ++s)  // ascending supernode order => fixed summation order
       for (int i = sn_w[s]; i < sn_h[s]; ++i) gl_idx[fill[rows[sn_rp[s] + i]]++] = uoff[s] + (i - sn_w[s]);
   }
-  // bottom of the forest as one launch per direction (opt-in): every supernode below level Lc belongs to the subtree of its
-  // highest ancestor that is still below Lc; all its descendants, hence everything its columns gather, are in that subtree
-  std::vector<BottomLevel> bot_lv;
-  std::vector<int> bot_cols, bot_fp, bot_bp;
-  if (const char* e = getenv("PREALPS_BJ_BOTTOM")) bj->bottom = std::max(0, std::min(atoi(e), nlev));
-  if (bj->bottom > 0) {
-    const int Lc = bj->bottom;
-    std::vector<int> root(ns, -1), sub_of(ns, -1);
-    int nsub = 0;
+  // ---- dataflow apply: dependencies of every panel, assembly tasks, and ALL work units of one apply in ticket order.
+  // A unit only ever waits for units with a smaller ticket (assembly before the panels of its level, children one level
+  // below their parent, the backward sweep after the forward one), so the CTA that draws a ticket always finds its
+  // predecessors finished or running.
+  std::vector<WorkUnit> all;
+  std::vector<AsmTask> atasks;
+  {
+    auto nfwd = [&](int s) { return (sn_h[s] + 31) / 32; };
+    auto nbwd = [&](int s) { return (sn_w[s] + 31) / 32; };
+    std::vector<int> ftarget(ns, 0), natasks(ns, 0);
+    for (int s = 0; s < ns; ++s) if (sn_par[s] >= 0) ftarget[sn_par[s]] += nfwd(s);
+    // assembly tasks: a warp handles 8 columns at a time (t = 8) and walks a column's gather list 8 entries per round trip;
+    // a task is a run of such passes whose chain of dependent round trips stays short -- the few thousand columns at the top
+    // of the forest, with hundreds of update rows each, spread over the whole machine like one column per lane group
+    std::vector<std::vector<AsmTask>> sn_tasks(ns);
     for (int s = 0; s < ns; ++s) {
-      if (sn_lev[s] >= Lc) continue;
-      int r = s;
-      while (sn_par[r] >= 0 && sn_lev[sn_par[r]] < Lc) r = sn_par[r];
-      root[s] = r;
-      if (sub_of[r] < 0) sub_of[r] = nsub++;
+      if (nchild[s] == 0) continue;
+      int begin = 0, cost = 0;
+      for (int c = 0; c < sn_w[s]; c += 8) {
+        long long maxlen = 0;
+        for (int j = c; j < std::min(sn_w[s], c + 8); ++j) maxlen = std::max(maxlen, gl_ptr[sn_c0[s] + j + 1] - gl_ptr[sn_c0[s] + j]);
+        const int pc = 1 + (int)((maxlen + 7) / 8);
+        if (c > begin && (cost + pc > kAsmChain || c - begin >= kAsmCols)) {
+          sn_tasks[s].push_back({sn_c0[s] + begin, sn_c0[s] + c, 4 * s + 0, 0, 4 * s + 1, {0, 0, 0}});
+          begin = c; cost = 0;
+        }
+        cost += pc;
+      }
+      sn_tasks[s].push_back({sn_c0[s] + begin, sn_c0[s] + sn_w[s], 4 * s + 0, 0, 4 * s + 1, {0, 0, 0}});
+      natasks[s] = (int)sn_tasks[s].size();
     }
-    bj->nsubtrees = nsub;
-    // bucket supernodes and panels by (subtree, level); inside a bucket: supernodes ascending, panels in panel order
-    std::vector<std::vector<int>> sn_b((size_t)nsub * Lc), fp_b((size_t)nsub * Lc), bp_b((size_t)nsub * Lc);
-    for (int s = 0; s < ns; ++s)
-      if (root[s] >= 0) sn_b[(size_t)sub_of[root[s]] * Lc + sn_lev[s]].push_back(s);
     for (size_t i = 0; i < fp.size(); ++i) {
       const int s = fp_sn[i];
-      if (root[s] >= 0) fp_b[(size_t)sub_of[root[s]] * Lc + sn_lev[s]].push_back((int)i);
+      if (nchild[s] > 0) { fp[i].dep = 4 * s + 1; fp[i].dep_target = natasks[s]; }
+      else fp[i].flags = 1;
+      fp[i].sig = sn_par[s] >= 0 ? 4 * sn_par[s] + 0 : 4 * s + 3;
     }
     for (size_t i = 0; i < bp.size(); ++i) {
-      const int s = bp_sn[i];
-      if (root[s] >= 0) bp_b[(size_t)sub_of[root[s]] * Lc + sn_lev[s]].push_back((int)i);
+      const int s = bp_sn[i], par = sn_par[s];
+      bp[i].dep = par >= 0 ? 4 * par + 2 : 4 * s + 3;
+      bp[i].dep_target = par >= 0 ? nbwd(par) : nfwd(s);
+      bp[i].sig = 4 * s + 2;
     }
-    bot_lv.resize((size_t)nsub * Lc);
-    for (size_t k = 0; k < bot_lv.size(); ++k) {
-      BottomLevel& L = bot_lv[k];
-      L.c0 = (int)bot_cols.size();
-      for (int s : sn_b[k])
-        for (int c = 0; c < sn_w[s]; ++c) bot_cols.push_back(sn_c0[s] + c);
-      L.c1 = (int)bot_cols.size();
-      L.f0 = (int)bot_fp.size();
-      bot_fp.insert(bot_fp.end(), fp_b[k].begin(), fp_b[k].end());
-      L.f1 = (int)bot_fp.size();
-      L.b0 = (int)bot_bp.size();
-      bot_bp.insert(bot_bp.end(), bp_b[k].begin(), bp_b[k].end());
-      L.b1 = (int)bot_bp.size();
+    int slot_base = 0, ctr_base = 0;
+    auto add_units = [&](const std::vector<WorkUnit>& src, int u0, int u1, int type) {
+      int slots = 0, ctrs = 0;
+      for (int i = u0; i < u1; ++i) {
+        WorkUnit u = src[i];
+        u.type = type;
+        if (u.split == 2) {
+          slots = std::max(slots, u.slot + u.nchunks);
+          ctrs = std::max(ctrs, u.cidx + 1);
+          u.slot += slot_base;
+          u.cidx += ctr_base;
+        }
+        all.push_back(u);
+      }
+      slot_base += slots;
+      ctr_base += ctrs;
+    };
+    auto add_tiny = [&](int first, int count, int type) {
+      for (int i = 0; i < count; i += kTinyUnit) all.push_back({first + i, std::min(kTinyUnit, count - i), 0, 0, 0, 0, 1, 0, 0, type});
+    };
+    for (int l = 0; l < nlev; ++l) {
+      const int t0 = (int)atasks.size();
+      for (int q = lev_ptr[l]; q < lev_ptr[l + 1]; ++q) {
+        const int s = order[q];
+        for (AsmTask tk : sn_tasks[s]) { tk.dep_target = ftarget[s]; atasks.push_back(tk); }
+      }
+      for (int i = t0; i < (int)atasks.size(); i += 8) all.push_back({i, std::min(8, (int)atasks.size() - i), 0, 0, 0, 0, 1, 0, 0, kUnitAsm});
+      add_units(fu, bj->fwd_unit_ptr[l], bj->fwd_unit_ptr[l + 1], kUnitFwd);
+      add_tiny(bj->fwd_tiny0[l], bj->fwd_tinyn[l], kUnitFwdTiny);
     }
+    for (int l = nlev - 1; l >= 0; --l) {
+      add_units(bu, bj->bwd_unit_ptr[l], bj->bwd_unit_ptr[l + 1], kUnitBwd);
+      add_tiny(bj->bwd_tiny0[l], bj->bwd_tinyn[l], kUnitBwdTiny);
+    }
+    bj->all_slots = slot_base;
+    bj->all_counters = ctr_base;
+    bj->n_all_units = (int)all.size();
+    bj->dep_ints = 4ll * ns + 8;
   }
   bj->stat[7] = now_s() - t_an0;
 
@@ -747,9 +783,8 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       upload(&bj->bwd_units, bu) || upload(&bj->perm, perm) || upload(&bj->rows, rows) ||
       upload(&bj->lvl_cols, lvl_cols) || upload(&bj->gl_ptr, gl_ptr) || upload(&bj->gl_idx, gl_idx))
     return 1;
-  if (bj->bottom > 0 && (upload(&bj->bot_lv, bot_lv) || upload(&bj->bot_cols, bot_cols) || upload(&bj->bot_fp, bot_fp) ||
-                         upload(&bj->bot_bp, bot_bp)))
-    return 1;
+  if (upload(&bj->all_units, all) || upload(&bj->asm_tasks, atasks)) return 1;
+  PCU_CUDA(cudaMalloc(&bj->dep, sizeof(int) * (size_t)bj->dep_ints));
 
   // ---------------------------------------------------------------- numeric factorisation
   cudaStream_t st = ctx->stream;

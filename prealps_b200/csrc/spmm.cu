@@ -21,13 +21,6 @@
 
 namespace {
 
-template <int T, int CPL>
-void launch_lean_nb(const SpmmArgs& a, int nblk, int nb, cudaStream_t st) {
-  if (nb >= 4) spmm_lean_kernel<T, CPL, 4, 4><<<nblk, kThreads, 0, st>>>(a);
-  else if (nb >= 2) spmm_lean_kernel<T, CPL, 2, 5><<<nblk, kThreads, 0, st>>>(a);
-  else spmm_lean_kernel<T, CPL, 1, 0><<<nblk, kThreads, 0, st>>>(a);  // MINB = 0: same as the bare bound
-}
-
 template <int T>
 void launch_bulk(const SpmmArgs& a, int nblk, bool wide, bool halo, cudaStream_t st) {
   if (wide) {
@@ -39,12 +32,6 @@ void launch_bulk(const SpmmArgs& a, int nblk, bool wide, bool halo, cudaStream_t
   }
 }
 
-template <int T>
-void launch_lean(const SpmmArgs& a, int nblk, bool wide, int nb, cudaStream_t st) {
-  if (wide) launch_lean_nb<T, 4>(a, nblk, nb, st);
-  else launch_lean_nb<T, 2>(a, nblk, nb, st);
-}
-
 // one CSR on the device with its row blocks
 struct CsrDev {
   int* rowPtr = nullptr;
@@ -53,7 +40,7 @@ struct CsrDev {
   int4* blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
   int nblk[2] = {0, 0};
   int64_t nnz = 0;
-  bool fits0 = true;  // every shape-0 row block fits the staging buffer (spmm_lean_kernel needs that)
+  bool fits0 = true;  // every shape-0 row block fits the staging buffer (spmm_bulk_kernel needs that)
 };
 
 int upload_csr(int m, const int* rowPtr, const int* colInd, const double* val, CsrDev* d) {
@@ -91,8 +78,7 @@ struct pcu_spmm {
   int m = 0, nhalo = 0;
   int64_t nnz = 0;
   CsrDev A;           // the local row panel, columns >= m read the halo buffer
-  int lean = 0;       // PREALPS_SPMM_LEAN=1|2|4 (gathers in flight per lane): spmm_lean_kernel from t = 8 up
-  bool bulk = false;  // PREALPS_SPMM_BULK=1: spmm_bulk_kernel (cp.async.bulk staging) from t = 8 up
+  bool bulk = true;   // spmm_bulk_kernel (cp.async.bulk staging) from t = 8 up; PREALPS_SPMM_BULK=0 keeps spmm_kernel (A/B runs)
   // PREALPS_SPMM_OVERLAP=1 and nhalo > 0: the panel split into its entries with column < m (Aloc, same rows) and the halo
   // entries of the boundary rows; the halo exchange then runs on comm_stream next to the local kernel
   bool overlap = false;
@@ -146,7 +132,6 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
     PCU_CHECK(colInd[p] >= 0 && colInd[p] < m + nhalo, "pcu_spmm_create: column index %d out of range at %lld",
               colInd[p], (long long)p);
   if (upload_csr(m, rowPtr, colInd, val, &op->A)) return 1;
-  if (const char* e = getenv("PREALPS_SPMM_LEAN")) op->lean = std::max(0, atoi(e));
   if (const char* e = getenv("PREALPS_SPMM_BULK")) op->bulk = atoi(e) != 0;
   if (getenv("PREALPS_SPMM_OVERLAP") != nullptr && nhalo > 0) {
     // split: Aloc keeps the entries with column < m of every row; (brow, hptr, hcol, hval) the others
@@ -268,21 +253,12 @@ static int launch_spmm(pcu_spmm* op, const CsrDev& A, const double* X, int ldx, 
   // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
   const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
                     ((uintptr_t)op->d_halo % 32 == 0) && A.nnz <= 12 * (int64_t)op->m;
-  const bool lean = op->lean > 0 && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
   const bool bulk = op->bulk && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
   if (bulk) {
     const bool halo = (&A == &op->A) && op->nhalo > 0;  // the local part of the overlapped product has no column >= m
     if (t == 8) launch_bulk<8>(a, nblk, wide, halo, c->stream);
     else if (t == 16) launch_bulk<16>(a, nblk, wide, halo, c->stream);
     else launch_bulk<32>(a, nblk, wide, halo, c->stream);
-  } else if (lean) {
-    // the lean kernel also takes the 4-columns-per-lane mapping for long rows when a row block still has a row for every
-    // lane group (27-point stencil: 56 rows per block, 32 groups at t = 32)
-    const bool align32 = (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) && ((uintptr_t)op->d_halo % 32 == 0);
-    const bool wide_lean = wide || (align32 && (int64_t)(kThreads / (t / 4)) * nblk <= (int64_t)op->m);
-    if (t == 8) launch_lean<8>(a, nblk, wide_lean, op->lean, c->stream);
-    else if (t == 16) launch_lean<16>(a, nblk, wide_lean, op->lean, c->stream);
-    else launch_lean<32>(a, nblk, wide_lean, op->lean, c->stream);
   } else if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {

@@ -138,99 +138,8 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
   }
 }
 
-// Candidate kernel, opt-in with PREALPS_SPMM_LEAN=1 (written after the last GPU session of round 1: compiled and its
-// SASS read, NOT yet run on a B200 -- measure before making it the default).  Same mapping, same summation order
-// and therefore the same bits as spmm_kernel<T, CPL>; what changes is the work per entry in the row phase.  The
-// SASS of spmm_kernel<8, 4> spends ~22 instructions per entry and lane: LDS col, LDS val, a compare, 4-5 predicated
-// LDC of the kernel arguments, two predicated IMAD.WIDE, four predicated LEA, a 64-bit add, LDG.256 and 4 DFMA.
-// Here the thread that stages an entry (once per entry, 32 entries per warp instruction) resolves "block row or
-// halo row" and the row stride into ONE 64-bit byte offset relative to X, stored next to the value, so the row phase
-// is LDS.128 + 64-bit add + LDG + CPL DFMA per entry.  Needs ldx == T (rows of X and of the halo buffer are both
-// T doubles apart) and every row block of shape 0 within the staging capacity.
-// NB > 1 (PREALPS_SPMM_LEAN=2 or 4): the gathers of NB consecutive entries of a row are issued back to back before
-// their FMAs (which keep their order).  ptxas only schedules them that way when __launch_bounds__ names a minimum
-// number of CTAs per SM (MINB): with the bare (256) bound it aims at 32 registers / full occupancy and sinks every load
-// next to its consumer -- one gather in flight per lane, which is also what spmm_kernel does.  NB = 2: <= 48 registers,
-// 5 CTAs/SM; NB = 4: <= 64 registers, 4 CTAs/SM.
-template <int T, int CPL, int NB, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) spmm_lean_kernel(SpmmArgs a) {
-  static_assert(CPL == 2 || CPL == 4, "lanes own 2 or 4 adjacent columns");
-  constexpr int G = T / CPL;
-  constexpr int NG = kThreads / G;
-  constexpr int kCap = kShapeNnz[0];
-  __shared__ double2 s_ent[kCap];  // {value, bit pattern of the source row's byte offset from X}
-  __shared__ int s_rp[kShapeRows[0] + 1];
-
-  const int4 d = __ldg(a.blk + blockIdx.x);
-  const int r0 = d.x, r1 = d.y, p0 = d.z, p1 = d.w;
-  const int n = p1 - p0;  // <= kCap: checked on the host before this kernel is chosen
-  const int tid = threadIdx.x;
-  // halo row c - m lives at H + (c - m) * T doubles = X + hdelta + c * T * 8 bytes (unused without a halo: c < m)
-  const long long hdelta = (long long)(reinterpret_cast<intptr_t>(a.H) - reinterpret_cast<intptr_t>(a.X)) -
-                           (long long)a.m * (T * 8);
-  for (int i = tid; i < n; i += kThreads) {
-    const int c = __ldg(a.colInd + p0 + i);
-    const long long off = (long long)c * (T * 8) + (c < a.m ? 0ll : hdelta);
-    s_ent[i] = make_double2(__ldg(a.val + p0 + i), __longlong_as_double(off));
-  }
-  for (int i = tid; i <= r1 - r0; i += kThreads) s_rp[i] = __ldg(a.rowPtr + r0 + i) - p0;
-  __syncthreads();
-  const int grp = tid / G, lig = tid % G;
-  const char* xl = reinterpret_cast<const char*>(a.X + CPL * lig);
-  for (int r = r0 + grp; r < r1; r += NG) {
-    const int b = s_rp[r - r0], e = s_rp[r - r0 + 1];
-    double acc[CPL];
-#pragma unroll
-    for (int j = 0; j < CPL; ++j) acc[j] = 0.0;
-    int p = b;
-    if constexpr (NB > 1) {
-      for (; p + NB <= e; p += NB) {
-        double2 en[NB];
-        double x[NB][4];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) en[k] = s_ent[p + k];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          const double* src = reinterpret_cast<const double*>(xl + __double_as_longlong(en[k].y));
-          if constexpr (CPL == 4) {
-            ldg4(src, x[k]);
-          } else {
-            const double2 v = ldg2(src);
-            x[k][0] = v.x;
-            x[k][1] = v.y;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < NB; ++k)
-#pragma unroll
-          for (int j = 0; j < CPL; ++j) acc[j] = fma(en[k].x, x[k][j], acc[j]);
-      }
-    }
-#pragma unroll 4
-    for (; p < e; ++p) {
-      const double2 en = s_ent[p];
-      const double* src = reinterpret_cast<const double*>(xl + __double_as_longlong(en.y));
-      if constexpr (CPL == 4) {
-        double x[4];
-        ldg4(src, x);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fma(en.x, x[j], acc[j]);
-      } else {
-        const double2 x = ldg2(src);
-        acc[0] = fma(en.x, x.x, acc[0]);
-        acc[1] = fma(en.x, x.y, acc[1]);
-      }
-    }
-    double* dst = a.Y + (size_t)r * a.ldy + CPL * lig;
-    if constexpr (CPL == 4) {
-      stg4(dst, acc);
-    } else {
-      *reinterpret_cast<double2*>(dst) = make_double2(acc[0], acc[1]);
-    }
-  }
-}
-
-// ---- bulk-copy staging (opt-in, PREALPS_SPMM_BULK=1; written after the last GPU session of round 1, not measured yet)
+// ---- bulk-copy staging (the default from t = 8 up; measured on B200 against the LDG + STS staging of spmm_kernel:
+// 7-point 128^3 t = 8: 109 -> 102 us, 27-point: 304 -> 256 us, profiles/r02_candidates_ab.md)
 #ifndef PCU_EMUL
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {

@@ -38,16 +38,13 @@ void emul_run_block(int block, void (*thunk)(void*), void* ctx) {
 
 namespace {
 
-// variant codes of the tests: 0 default kernel, 1 / 2 / 4 lean with that many gathers in flight, 8 / 9 bulk-copy staging
-// (9: HALO = false, for operators without a column >= m)
+// variant codes of the tests: 0 LDG + STS staging (spmm_kernel), 8 / 9 bulk-copy staging (spmm_bulk_kernel; 9: HALO = false,
+// for operators without a column >= m)
 template <int T, int CPL>
 void run_variant(int lean, const SpmmArgs& a, int nblk) {
   if (lean == 8) { emul_launch(nblk, kThreads, [&] { spmm_bulk_kernel<T, CPL, true>(a); }); return; }
   if (lean == 9) { emul_launch(nblk, kThreads, [&] { spmm_bulk_kernel<T, CPL, false>(a); }); return; }
-  if (lean >= 4) emul_launch(nblk, kThreads, [&] { spmm_lean_kernel<T, CPL, 4, 4>(a); });
-  else if (lean >= 2) emul_launch(nblk, kThreads, [&] { spmm_lean_kernel<T, CPL, 2, 5>(a); });
-  else if (lean == 1) emul_launch(nblk, kThreads, [&] { spmm_lean_kernel<T, CPL, 1, 0>(a); });
-  else emul_launch(nblk, kThreads, [&] { spmm_kernel<T, CPL>(a); });
+  emul_launch(nblk, kThreads, [&] { spmm_kernel<T, CPL>(a); });
 }
 
 // Y = A [X ; H] with the kernel spmm.cu: launch_spmm would pick for (t, cpl, lean); cpl = 0: the generic kernel
@@ -58,7 +55,7 @@ int run_spmm(int lean, int cpl, int m, const int* rowPtr, const int* colInd, con
   build_row_blocks(m, rowPtr, sh, &blk);
   if (lean > 0) {
     if (t < 8 || ldx != t) return 2;
-    for (const int4& b : blk) if (b.w - b.z > kShapeNnz[0]) return 3;  // the host would not choose the lean kernel
+    for (const int4& b : blk) if (b.w - b.z > kShapeNnz[0]) return 3;  // the host would not choose the bulk kernel
   }
   // like upload_csr: 16 bytes of slack behind the entries (the bulk copies round their size up), 16-byte aligned starts
   const int nnz = rowPtr[m];

@@ -111,79 +111,47 @@ def test_indefinite_block_is_rejected(emul):
     assert rc == 2 and b"not positive definite" in lib.pcu_last_error()
 
 
-def test_graph_candidate_replays_the_same_chain(emul, monkeypatch):
-    """PREALPS_BJ_GRAPH=1: first use of an argument tuple runs directly, the second captures + launches, later ones replay;
-    growing the work vectors (a wider solve) drops the captured graphs"""
-    lib, ctx = emul
-    lib.emul_graph_replay_count.restype = C.c_longlong
-    lib.emul_launch_count.restype = C.c_longlong
-    A = gen_matrices.poisson7(5).tocsr()
-    n = A.shape[0]
-    rc, bj, cuts, blocks = factor(emul, A, 1)
-    assert rc == 0
-    B4 = np.random.default_rng(4).standard_normal((n, 4))
-    X4 = np.zeros((n, 4))
-    monkeypatch.delenv("PREALPS_BJ_GRAPH", raising=False)
-    assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0
-    base, l0 = X4.copy(), lib.emul_launch_count(ctx)
-    assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0
-    per_apply = lib.emul_launch_count(ctx) - l0
-    monkeypatch.setenv("PREALPS_BJ_GRAPH", "1")
-    r0 = lib.emul_graph_replay_count()
-    for k in range(4):
-        X4[:] = 0
-        l0 = lib.emul_launch_count(ctx)
-        assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0, lib.pcu_last_error()
-        assert np.array_equal(X4, base)
-        assert lib.emul_launch_count(ctx) - l0 == per_apply  # the launch counter keeps counting kernels
-        replays = lib.emul_graph_replay_count() - r0
-        assert (replays == 0) if k == 0 else (replays > 0)
-        r0 = lib.emul_graph_replay_count()
-    # a wider solve re-allocates the work vectors: the old graph must not be replayed into freed memory
-    B16 = np.random.default_rng(16).standard_normal((n, 16))
-    X16 = np.zeros((n, 16))
-    for k in range(3):
-        assert lib.pcu_bj_apply(bj, dp(B16), 16, dp(X16), 16, 16) == 0
-    ref = direct(blocks, cuts, B16)
-    assert np.linalg.norm(X16 - ref) <= 1e-12 * np.linalg.norm(ref)
-    for k in range(3):
-        X4[:] = 0
-        assert lib.pcu_bj_apply(bj, dp(B4), 4, dp(X4), 4, 4) == 0
-        assert np.array_equal(X4, base)
-    lib.pcu_bj_destroy(bj)
-
-
-@pytest.mark.parametrize("nblk,t", [(2, 8), (1, 3)])
-def test_bottom_of_forest_candidate_is_bit_identical(emul, monkeypatch, nblk, t):
-    """PREALPS_BJ_BOTTOM=Lc: levels [0, Lc) as one forward and one backward launch, a CTA per subtree; same operation order
-    per panel and per gather list as the level-by-level kernels, far fewer launches"""
+@pytest.mark.parametrize("gen,N,nblk,t", [("poisson7", 6, 2, 8), ("poisson7", 7, 1, 3), ("stencil27", 5, 2, 16), ("poisson7", 6, 3, 1)])
+def test_dataflow_apply_is_bit_identical_to_the_level_by_level_launches(emul, monkeypatch, gen, N, nblk, t):
+    """the default apply is ONE persistent launch whose work units wait on per-supernode counters (bj_solve.cu: apply_kernel);
+    PREALPS_BJ_LEVELS=1 is the launch group per level it replaces.  Same operation order per panel and per gather list:
+    same bits.  (The emulation runs the CTAs one after the other, so the first draws every ticket in order: this checks
+    the unit list, the dependency targets -- an unmet one aborts -- and the index logic, not the concurrency.)"""
     lib, ctx = emul
     lib.emul_launch_count.restype = C.c_longlong
-    A = gen_matrices.poisson7(6).tocsr()
+    A = getattr(gen_matrices, gen)(N).tocsr()
     n = A.shape[0]
-    ld = t if t % 2 == 0 else t + 1
+    ld = t if (t % 2 == 0 or t == 1) else t + 1
     B = np.random.default_rng(t).standard_normal((n, ld))
+    rc, bj, cuts, blocks = factor(emul, A, nblk)
+    assert rc == 0, lib.pcu_last_error()
     out, launches = {}, {}
-    for Lc in (0, 2, 99):
-        if Lc:
-            monkeypatch.setenv("PREALPS_BJ_BOTTOM", str(Lc))
+    for mode in ("levels", "dataflow", "dataflow"):
+        if mode == "levels":
+            monkeypatch.setenv("PREALPS_BJ_LEVELS", "1")
         else:
-            monkeypatch.delenv("PREALPS_BJ_BOTTOM", raising=False)
-        rc, bj, cuts, blocks = factor(emul, A, nblk)
-        assert rc == 0, lib.pcu_last_error()
+            monkeypatch.delenv("PREALPS_BJ_LEVELS", raising=False)
         X = np.full((n, ld), np.nan)
         l0 = lib.emul_launch_count(ctx)
         assert lib.pcu_bj_apply(bj, dp(B), ld, dp(X), ld, t) == 0, lib.pcu_last_error()
-        launches[Lc] = lib.emul_launch_count(ctx) - l0
-        out[Lc] = X[:, :t].copy()
+        launches[mode] = lib.emul_launch_count(ctx) - l0
+        if mode in out:
+            assert np.array_equal(out[mode], X[:, :t])  # the counters are reset between applies
+        out[mode] = X[:, :t].copy()
         B2 = B.copy()  # in place
         assert lib.pcu_bj_apply(bj, dp(B2), ld, dp(B2), ld, t) == 0
-        assert np.array_equal(B2[:, :t], out[Lc])
-        lib.pcu_bj_destroy(bj)
+        assert np.array_equal(B2[:, :t], out[mode])
     ref = direct(blocks, cuts, B[:, :t])
-    assert np.linalg.norm(out[0] - ref) <= 1e-12 * np.linalg.norm(ref)
-    assert np.array_equal(out[2], out[0]) and np.array_equal(out[99], out[0])
-    assert launches[99] == 2 and launches[99] < launches[2] < launches[0]
+    assert np.linalg.norm(out["levels"] - ref) <= 1e-12 * np.linalg.norm(ref)
+    assert np.array_equal(out["dataflow"], out["levels"])
+    assert launches["dataflow"] == 1 and launches["levels"] > 4
+    # an unaligned caller block takes the scalar path for the rows of childless supernodes
+    Bu = np.zeros(n * ld + 1)
+    Bu[1:] = B.ravel()
+    X = np.full((n, ld), np.nan)
+    assert lib.pcu_bj_apply(bj, dp(Bu[1:]), ld, dp(X), ld, t) == 0
+    assert np.array_equal(X[:, :t], out["levels"])
+    lib.pcu_bj_destroy(bj)
 
 
 def test_kernels_under_address_sanitizer():

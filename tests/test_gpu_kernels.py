@@ -61,22 +61,19 @@ candidates = pytest.mark.skipif(not os.environ.get("PREALPS_TEST_CANDIDATES"),
                                 reason="opt-in kernels that have not been measured on a B200 yet (PREALPS_TEST_CANDIDATES=1)")
 
 
-@candidates
 @pytest.mark.parametrize("gen,N", [("poisson7", 14), ("stencil27", 9)])
-def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
-    """PREALPS_SPMM_LEAN=1|2|4 (spmm_lean_kernel, 1, 2 or 4 gathers in flight per lane) and PREALPS_SPMM_BULK=1
-    (spmm_bulk_kernel, cp.async.bulk staging) keep the mapping and the summation order: same bits as the default kernel"""
+def test_spmm_bulk_staging_is_bit_identical(dev, gen, N, monkeypatch):
+    """spmm_bulk_kernel (cp.async.bulk staging, the default from t = 8 up) keeps the mapping and the summation order of
+    spmm_kernel (PREALPS_SPMM_BULK=0): same bits"""
     A = getattr(gen_matrices, gen)(N).tocsr()
     m = A.shape[0]
     nh = 53
     B = sp.random(m, nh, density=0.03, random_state=5, format="csr")
     Aext = sp.hstack([A, B]).tocsr()
     Aext.sort_indices()
-    rng = np.random.default_rng(1)
     out = {}
-    for lean in ("0", "1", "2", "4", "bulk"):
-        monkeypatch.setenv("PREALPS_SPMM_LEAN", "0" if lean == "bulk" else lean)
-        monkeypatch.setenv("PREALPS_SPMM_BULK", "1" if lean == "bulk" else "0")
+    for bulk in ("0", "1"):
+        monkeypatch.setenv("PREALPS_SPMM_BULK", bulk)
         op = C.c_void_p()
         assert cu.pcu_spmm_create(dev.ctx, m, nh, capi.ip(Aext.indptr.astype(np.int32)), capi.ip(Aext.indices.astype(np.int32)),
                                   capi.dp(Aext.data), C.byref(op)) == 0, cu.pcu_last_error()
@@ -90,14 +87,13 @@ def test_spmm_lean_candidate_is_bit_identical(dev, gen, N, monkeypatch):
             assert cu.pcu_h2d(dev.ctx, C.c_void_p(hb), H.ctypes.data_as(C.c_void_p), C.c_size_t(H.nbytes)) == 0
             dX, dY = dev.up(X), dev.zeros(m * t)
             assert cu.pcu_spmm_apply(op, dX, t, dY, t, t) == 0, cu.pcu_last_error()
-            out[lean, t] = dev.down(dY, (m, t))
+            out[bulk, t] = dev.down(dY, (m, t))
             ref = Aext @ np.vstack([X, H])
-            assert np.allclose(out[lean, t], ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+            assert np.allclose(out[bulk, t], ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
             dev.free(dX, dY)
         cu.pcu_spmm_destroy(op)
     for t in (8, 16, 32):
-        for lean in ("1", "2", "4", "bulk"):
-            assert np.array_equal(out["0", t], out[lean, t])
+        assert np.array_equal(out["0", t], out["1", t])
 
 
 def test_spmm_long_rows_and_empty_rows(dev):
@@ -241,79 +237,47 @@ def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t):
     cu.pcu_bj_destroy(bj)
 
 
-@candidates
-@pytest.mark.parametrize("var", ["PREALPS_BJ_ASM_PREFETCH", "PREALPS_BJ_GRAPH"])
-@pytest.mark.parametrize("t", [1, 8, 16])
-def test_block_jacobi_candidates_are_bit_identical(dev, t, var, monkeypatch):
-    """PREALPS_BJ_ASM_PREFETCH=1 only moves loads of static data in front of griddepcontrol.wait; PREALPS_BJ_GRAPH=1 replays
-    the same launch chain from a CUDA graph (captured on the second use of an argument tuple): same bits"""
-    A = gen_matrices.poisson7(20).tocsr()
-    n = A.shape[0]
-    cuts = np.array([0, n // 2, n], dtype=np.int32)
-    keep = []
-    for b in range(2):
-        U = sp.triu(A[cuts[b]:cuts[b + 1], cuts[b]:cuts[b + 1]], format="csr")
-        U.sort_indices()
-        keep.append((U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data.copy()))
-    rp = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[0]) for k in keep])
-    ci = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[1]) for k in keep])
-    vv = (C.POINTER(C.c_double) * 2)(*[capi.dp(k[2]) for k in keep])
-    bj = C.c_void_p()
-    assert cu.pcu_bj_create(dev.ctx, 2, capi.ip(cuts), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
-    B = np.random.default_rng(t).standard_normal((n, t))
-    dB, dX = dev.up(B), dev.zeros(n * t)
-    out = []
-    for flag in (None, "1", "1", "1", None, "1"):
-        if flag is None:
-            monkeypatch.delenv(var, raising=False)
-        else:
-            monkeypatch.setenv(var, flag)
-        assert cu.pcu_bj_apply(bj, dB, t, dX, t, t) == 0, cu.pcu_last_error()
-        out.append(dev.down(dX, (n, t)))
-    for o in out[1:]:
-        assert np.array_equal(o, out[0])
-    dev.free(dB, dX)
-    cu.pcu_bj_destroy(bj)
-
-
-@candidates
-@pytest.mark.parametrize("t", [1, 8, 16])
-def test_block_jacobi_bottom_candidate(dev, t, monkeypatch):
-    """PREALPS_BJ_BOTTOM=Lc (read when the factor is created): levels [0, Lc) as one launch per direction.  Same operation
-    order per panel and gather list: bit-identical on the CPU emulation; on the GPU the DMMA order inside a k-block is the
-    hardware's either way, so equality is expected too and 1e-13 is asserted"""
+@pytest.mark.parametrize("t", [1, 3, 8, 16, 32])
+def test_block_jacobi_dataflow_apply_matches_the_level_by_level_launches(dev, t, monkeypatch):
+    """the default apply is ONE persistent launch whose work units wait on per-supernode counters (bj_solve.cu: apply_kernel);
+    PREALPS_BJ_LEVELS=1 is the launch group per level it replaces.  Same operation order per panel and per gather list:
+    same bits, on several subdomains and repeatedly (the counters are reset before every apply)."""
     import scipy.sparse.linalg as spla
-    A = gen_matrices.poisson7(16).tocsr()
+    A = gen_matrices.poisson7(24).tocsr()
     n = A.shape[0]
-    cuts = np.array([0, n // 2, n], dtype=np.int32)
-    blocks = [A[cuts[b]:cuts[b + 1], cuts[b]:cuts[b + 1]].tocsr() for b in range(2)]
+    nb = 3
+    cuts = np.linspace(0, n, nb + 1).astype(np.int32)
+    blocks = [A[cuts[b]:cuts[b + 1], cuts[b]:cuts[b + 1]].tocsr() for b in range(nb)]
     keep = []
     for Bk in blocks:
         U = sp.triu(Bk, format="csr")
         U.sort_indices()
         keep.append((U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data.copy()))
-    rp = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[0]) for k in keep])
-    ci = (C.POINTER(C.c_int) * 2)(*[capi.ip(k[1]) for k in keep])
-    vv = (C.POINTER(C.c_double) * 2)(*[capi.dp(k[2]) for k in keep])
-    B = np.random.default_rng(t).standard_normal((n, t))
-    ref = np.vstack([spla.splu(Bk.tocsc()).solve(B[cuts[b]:cuts[b + 1]]) for b, Bk in enumerate(blocks)])
-    out = {}
-    for Lc in (0, 3, 6, 99):
-        if Lc:
-            monkeypatch.setenv("PREALPS_BJ_BOTTOM", str(Lc))
+    rp = (C.POINTER(C.c_int) * nb)(*[capi.ip(k[0]) for k in keep])
+    ci = (C.POINTER(C.c_int) * nb)(*[capi.ip(k[1]) for k in keep])
+    vv = (C.POINTER(C.c_double) * nb)(*[capi.dp(k[2]) for k in keep])
+    bj = C.c_void_p()
+    assert cu.pcu_bj_create(dev.ctx, nb, capi.ip(cuts), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
+    ld = t if (t % 2 == 0 or t == 1) else t + 1
+    B = np.random.default_rng(t).standard_normal((n, ld))
+    dB, dX = dev.up(B), dev.zeros(n * ld)
+    out = []
+    for levels in ("1", None, None, "1", None):
+        if levels is None:
+            monkeypatch.delenv("PREALPS_BJ_LEVELS", raising=False)
         else:
-            monkeypatch.delenv("PREALPS_BJ_BOTTOM", raising=False)
-        bj = C.c_void_p()
-        assert cu.pcu_bj_create(dev.ctx, 2, capi.ip(cuts), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
-        dB, dX = dev.up(B), dev.zeros(n * t)
-        for rep in range(3):
-            assert cu.pcu_bj_apply(bj, dB, t, dX, t, t) == 0, cu.pcu_last_error()
-        out[Lc] = dev.down(dX, (n, t))
-        assert np.linalg.norm(out[Lc] - ref) < 1e-11 * np.linalg.norm(ref)
-        dev.free(dB, dX)
-        cu.pcu_bj_destroy(bj)
-    for Lc in (3, 6, 99):
-        assert np.abs(out[Lc] - out[0]).max() <= 1e-13 * np.abs(out[0]).max()
+            monkeypatch.setenv("PREALPS_BJ_LEVELS", levels)
+        assert cu.pcu_bj_apply(bj, dB, ld, dX, ld, t) == 0, cu.pcu_last_error()
+        out.append(dev.down(dX, (n, ld))[:, :t])
+    ref = np.vstack([spla.splu(Bk.tocsc()).solve(B[cuts[b]:cuts[b + 1], :t]) for b, Bk in enumerate(blocks)])
+    assert np.linalg.norm(out[0] - ref) <= 1e-11 * np.linalg.norm(ref)
+    for o in out[1:]:
+        assert np.array_equal(o, out[0])
+    monkeypatch.delenv("PREALPS_BJ_LEVELS", raising=False)
+    assert cu.pcu_bj_apply(bj, dB, ld, dB, ld, t) == 0   # in place
+    assert np.array_equal(dev.down(dB, (n, ld))[:, :t], out[0])
+    dev.free(dB, dX)
+    cu.pcu_bj_destroy(bj)
 
 
 def test_block_jacobi_long_panels_cut_across_ctas(dev):

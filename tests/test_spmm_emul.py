@@ -1,6 +1,6 @@
 """The SpMM kernels of prealps_b200/csrc/spmm_kernels.cuh executed on the CPU by tests/emul (one pthread per CUDA thread):
-index logic of every template instantiation against scipy, and of the opt-in candidates (lean row phase with 1, 2 or 4
-gathers in flight, local/halo split of the overlapped product) bit for bit against the default kernels.  TEST
+index logic of every template instantiation against scipy; the bulk-staging kernels and the local/halo split of the
+overlapped product bit for bit against the LDG + STS staging kernel.  TEST
 INFRASTRUCTURE: the emulation is compiled here into tests/_build and is not part of the product libraries; what it cannot
 see (PTX semantics, alignment traps beyond the asserted ones, timing) is left to the -m gpu tests."""
 import ctypes as C
@@ -101,23 +101,23 @@ def test_long_and_empty_rows(emul):
         Y = run(emul, "merged", 0, cpl, mm, rp, ci, v, X, H, t, t)
         ref = A @ np.vstack([X, H])
         assert np.allclose(Y, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
-    # the host never picks the lean kernel when a row block exceeds the staging buffer
+    # the host never picks the bulk-staging kernel when a row block exceeds the staging buffer
     X, H = inputs(mm, nh, 8, 8, 1)
     Y = aligned((mm, 8))
-    assert emul.emul_spmm(1, 4, mm, ip(rp), ip(ci), dp(v), dp(X), 8, dp(H), dp(Y), 8, 8) == 3
+    assert emul.emul_spmm(8, 4, mm, ip(rp), ip(ci), dp(v), dp(X), 8, dp(H), dp(Y), 8, 8) == 3
 
 
 @pytest.mark.parametrize("gen,N", [("poisson7", 11), ("stencil27", 7)])
 @pytest.mark.parametrize("t", [8, 16, 32])
 @pytest.mark.parametrize("cpl", [2, 4])
-def test_lean_candidates_are_bit_identical(emul, gen, N, t, cpl):
-    """PREALPS_SPMM_LEAN=1|2|4: byte offsets resolved at staging time, 1 / 2 / 4 gathers in flight per lane"""
+def test_bulk_staging_is_bit_identical(emul, gen, N, t, cpl):
+    """spmm_bulk_kernel (cp.async.bulk staging, the default from t = 8 up) against spmm_kernel (LDG + STS staging)"""
     Aext, m, rp, ci, v = operator(gen, N, 41)
     X, H = inputs(m, 41, t, t, t + cpl)
     base = run(emul, "merged", 0, cpl, m, rp, ci, v, X, H, t, t)
     ref = Aext @ np.vstack([X, H])
     assert np.allclose(base, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
-    for lean in (1, 2, 4, 8):  # 8: PREALPS_SPMM_BULK=1, cp.async.bulk staging (HALO = true)
+    for lean in (8,):  # cp.async.bulk staging, HALO = true
         Y = run(emul, "merged", lean, cpl, m, rp, ci, v, X, H, t, t)
         assert np.array_equal(Y, base), (lean, np.abs(Y - base).max())
 
@@ -139,7 +139,7 @@ def test_bulk_candidate_without_halo(emul, t, cpl):
     assert np.array_equal(Y, base)
 
 
-@pytest.mark.parametrize("t,cpl,lean", [(1, 1, 0), (4, 2, 0), (8, 4, 0), (8, 4, 1), (16, 2, 4), (32, 4, 2), (12, 0, 0), (8, 4, 9), (16, 2, 9)])
+@pytest.mark.parametrize("t,cpl,lean", [(1, 1, 0), (4, 2, 0), (8, 4, 0), (12, 0, 0), (8, 4, 9), (16, 2, 9), (32, 4, 9)])
 def test_local_halo_split_is_bit_identical(emul, t, cpl, lean):
     """PREALPS_SPMM_OVERLAP=1: local kernel on the entries with column < m, then halo_add_kernel continues the FMA chains"""
     Aext, m, rp, ci, v = operator("poisson7", 11, 37)
