@@ -35,7 +35,8 @@ int preAlps_b200_InitNccl(int nranks, int rank, const void* id128);   /* one pro
 int preAlps_b200_OperatorBuildCSR(int M, const int* rowPtr, const int* colInd, const double* val,
                                   int S, int s_lo, int s_hi, int scale, const int* parts_in);
 int preAlps_b200_OperatorBuildFile(const char* mtx, int S, int s_lo, int s_hi);
-/* synthetic operators of BASELINE.json: kind 0 = 7-point Poisson, 1 = 27-point stencil */
+/* synthetic operators of BASELINE.json: kind 0 = 7-point Poisson, 1 = 27-point stencil, 2 = Q1 linear
+ * elasticity on N^3 nodes (3 dof per node, the face x = 0 clamped) */
 int preAlps_b200_OperatorBuildStencil(int kind, int N, int S, int s_lo, int s_hi);
 /* block-Jacobi over all local subdomains of the current operator */
 int preAlps_b200_BlockJacobiCreate(void);

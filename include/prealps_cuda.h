@@ -136,7 +136,8 @@ int pcu_bj_analyze(int n, const int* rowPtr, const int* colInd, int use_metis, i
  * 3 tree levels, 4 bytes streamed per apply at width t=8, 5 factor flops,
  * 6 factor seconds (device), 7 analysis seconds (host), 8 kernel launches per apply */
 double pcu_bj_stat(pcu_bj* bj, int which);
-double pcu_bj_bytes(pcu_bj* bj, int t);   /* algorithmic bytes of one apply at width t */
+double pcu_bj_bytes(pcu_bj* bj, int t);   /* algorithmic bytes of one apply at width t: exact nnz(L), SURVEY.md 8(d) */
+double pcu_bj_stored_bytes(pcu_bj* bj, int t);   /* bytes the sweeps move: stored panels (zeros and padding included) + vectors */
 
 /* -------------------------------------- K4/K5/K6: fused tall-skinny kernels
  * All blocks row-major with leading dimension ld; small matrices (t x t) are

@@ -355,7 +355,11 @@ def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None, rrqr=False):
     """_preAlps_ECGIterateOdir / Omin with the driver loop (ecg.c:98-171,223-271,289-530;
     test_ecg_prealps_op.c:203-223), NO_BS_RED.  Global arrays; reductions summed over ranks in rank order
     like the oracle's MPI shim.  rrqr=True (Orthomin only) adds the ADAPT_BS branch of ecg.c:360-393 -- the
-    rank-revealing Cholesky QR of the new directions -- for the full-rank case."""
+    rank-revealing Cholesky QR of the new directions.  The reference is consistent up to and including its first rank
+    drop (pinned by the golden poisson7_n4_s4_t4_omin_adapt_rankdrop); afterwards it forms P^T P with the stale column
+    count of P's info (ecg.c:366 after the copy of nrhs columns at :357).  From there this follows what the reduction
+    stands for: every iteration the t new directions Z - P beta are orthonormalised again and `rank` of them are kept.
+    Returns bs_hist (block size after each iteration) as well."""
     S, rowPos, M = P.S, P.rowPos, P.Ap.shape[0]
     sizes = [rowPos[r + 1] - rowPos[r] for r in range(S)]
     if rhs is None:
@@ -418,6 +422,7 @@ def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None, rrqr=False):
         b = np.concatenate(rhs)
         return {"iter": it, "res_hist": np.array(hist), "sol": sol, "normb": normb,
                 "true_relres": np.linalg.norm(b - A @ sol) / np.linalg.norm(b), "rhs": rhs}
+    bs_hist = []
     while True:
         G = gsum(lambda r: AP[sl[r]].T @ Pk[sl[r]])                     # ecg.c:425-428
         U = sla.cholesky(np.triu(G) + np.triu(G, 1).T, lower=False)      # ecg.c:431 ('U' triangle)
@@ -429,7 +434,8 @@ def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None, rrqr=False):
         it += 1
         res = np.sqrt(np.trace(gsum(lambda r: R[sl[r]].T @ R[sl[r]])))   # ecg.c:250-261
         hist.append(res)
-        if not (res > normb * tol and it < max_iter):                    # ecg.c:264
+        bs_hist.append(Pk.shape[1])
+        if not (res > normb * tol and it < max_iter and Pk.shape[1] > 0):   # ecg.c:264
             break
         if ortho == 0:
             Z = prec(AP)                                                 # test_ecg_prealps_op.c:219
@@ -444,12 +450,11 @@ def ecg_solve(P, t, tol, max_iter=1000, ortho=0, rhs=None, rrqr=False):
             if rrqr:
                 C = gsum(lambda r: Pk[sl[r]].T @ Pk[sl[r]])              # ecg.c:366-372
                 Uf, piv, rank, info = sla.lapack.dpstrf(np.triu(C), lower=0, tol=-1.0)   # ecg.c:375
-                if rank < t:
-                    raise ValueError("rank drop: the reference's handling of this case is inconsistent")
-                Pk = sla.solve_triangular(np.triu(Uf), Pk[:, piv - 1].T, trans="T", lower=False).T  # ecg.c:380-383
+                Pk = sla.solve_triangular(np.triu(Uf)[:rank, :rank], Pk[:, piv[:rank] - 1].T, trans="T", lower=False).T  # ecg.c:380-391
+                # ecg.c:391 sets ecg->bs = rank: the driver sees it at the next stopping test (bs_hist above)
         AP = A @ Pk
     sol = X.sum(axis=1)                                                  # ecg.c:674
     b = np.concatenate(rhs)
     true_rel = np.linalg.norm(b - A @ sol) / np.linalg.norm(b)
     return {"iter": it, "res_hist": np.array(hist), "sol": sol, "normb": normb, "true_relres": true_rel,
-            "rhs": rhs}
+            "rhs": rhs, "bs_hist": np.array(bs_hist, dtype=np.int32)}

@@ -88,6 +88,7 @@ cuda.pcu_malloc.argtypes = [C.c_void_p, C.c_size_t]
 cuda.pcu_host_alloc.restype = C.c_void_p
 cuda.pcu_spmm_bytes.restype = C.c_double
 cuda.pcu_bj_bytes.restype = C.c_double
+cuda.pcu_bj_stored_bytes.restype = C.c_double
 cuda.pcu_bj_stat.restype = C.c_double
 cuda.pcu_launch_count.restype = C.c_int64
 cuda.pcu_ctx_stream.restype = C.c_void_p

@@ -22,12 +22,6 @@
 
 namespace pcu {
 
-// Dataflow apply (bj_solve.cu: apply_kernel): the whole apply is ONE persistent launch; what used to be a kernel boundary
-// between levels is a counter per supernode.  dep / dep_target: the counter a panel waits for (index into pcu_bj::dep, -1:
-// none) and the value it must reach; sig: the counter it increments when its outputs are in memory (-1: none).
-// Four counters per supernode s:  4s+0 finished forward panels of the children of s (the assembly of s waits for all),
-// 4s+1 finished assembly tasks of s (its forward panels wait), 4s+2 finished backward panels of s (the backward panels of
-// its children wait), 4s+3 finished forward panels of s itself (roots only: their backward panels wait).
 struct FwdPanel {      // one 32-row slice of M_s
   long long off;       // offset (doubles) into fwd_data
   long long uoff;      // first row of this supernode's slot in the update buffer U
@@ -35,9 +29,7 @@ struct FwdPanel {      // one 32-row slice of M_s
   int c0;              // first column of the supernode (forest index): input rows Wk[c0 .. c0+klen)
   int row0;            // first row of the slice inside the supernode (multiple of 32)
   int w, h;            // supernode width / height
-  int dep, dep_target, sig;
-  int flags;           // bit 0: supernode without children -- nothing to subtract, its input rows are read straight
-  int pad_;            //        from the caller's block (B[perm[c]]) and never pass through Wk
+  int pad_;
 };
 
 struct BwdPanel {      // one 32-row slice of M_s^T
@@ -47,20 +39,8 @@ struct BwdPanel {      // one 32-row slice of M_s^T
   int k0;              // = row0 (multiple of 32): first supernode row that contributes
   int c0;              // first column of the supernode
   int w, h;
-  int dep, dep_target, sig;
-  int pad0_, pad1_;
+  int pad_;
 };
-
-struct AsmTask {       // forward right-hand side of the forest columns [c_begin, c_end) of one supernode, one warp
-  int c_begin, c_end;
-  int dep, dep_target, sig;
-  int pad_[3];
-};
-
-enum UnitType { kUnitSweep = 0, kUnitAsm = 1, kUnitFwd = 2, kUnitFwdTiny = 3, kUnitBwd = 4, kUnitBwdTiny = 5 };
-constexpr int kAsmCols = 128;   // most columns per assembly task ...
-constexpr int kAsmChain = 8;    // ... and most dependent memory round trips (bj_factor.cu)
-constexpr int kTinyUnit = 32;   // tiny panels per work unit of the dataflow kernel (8 at a time, one per warp)
 
 constexpr int kTinyS = 16;  // ... and the very short ones get half of the buffer, 2x more warps per SM
 constexpr int kTinyK = 32;  // panels up to this many steps are staged whole into shared memory (64 was 3 % slower:
@@ -78,7 +58,7 @@ struct WorkUnit {      // one CTA of the sweep kernels
   int chunk, nchunks;  // split == 2: position of the slice; the CTA that finishes last adds the slices in order
   int slot;            // split == 2: first scratch slot of the panel (one slot = 32 x T doubles per slice); counter index in cidx
   int cidx;
-  int type;            // UnitType (dataflow kernel); kUnitSweep in the per-level lists
+  int pad_;
 };
 
 }  // namespace pcu
@@ -109,6 +89,7 @@ struct pcu_bj {
   int* rows = nullptr;             // forest row index of every supernode row (gather index of the backward sweep)
   int* lvl_cols = nullptr;         // forest columns sorted by level
   std::vector<int> lvl_col_ptr;    // per level, nlevels+1
+  std::vector<char> lvl_long_lists;  // per level: its columns gather > 16 update rows on average (assemble_kernel<T, 16>)
   long long* gl_ptr = nullptr;     // per forest column: range into gl_idx
   long long* gl_idx = nullptr;     // rows of U that must be subtracted from that column
   // work vectors (sized for cap_t columns)
@@ -121,11 +102,4 @@ struct pcu_bj {
   double* scratch = nullptr;
   int* counters = nullptr;
   int scratch_slots = 0, ncounters = 0;
-  // dataflow apply: every work unit of one apply in ticket order (forward levels up, then backward levels down)
-  pcu::WorkUnit* all_units = nullptr;
-  int n_all_units = 0;
-  pcu::AsmTask* asm_tasks = nullptr;
-  int* dep = nullptr;              // 4 counters per supernode + the ticket counter + an error flag, zeroed before every apply
-  long long dep_ints = 0;
-  int all_slots = 0, all_counters = 0;   // scratch slots / arrival counters when every level may be in flight at once
 };

@@ -357,7 +357,6 @@ int pcu_bj_destroy(pcu_bj* bj) {
   cudaFree(bj->fwd_data); cudaFree(bj->bwd_data); cudaFree(bj->fwd_panels); cudaFree(bj->bwd_panels);
   cudaFree(bj->fwd_units); cudaFree(bj->bwd_units); cudaFree(bj->perm); cudaFree(bj->rows);
   cudaFree(bj->lvl_cols); cudaFree(bj->gl_ptr); cudaFree(bj->gl_idx);
-  cudaFree(bj->all_units); cudaFree(bj->asm_tasks); cudaFree(bj->dep);
   cudaFree(bj->Wk); cudaFree(bj->Y); cudaFree(bj->U); cudaFree(bj->Xp); cudaFree(bj->scratch); cudaFree(bj->counters);
   delete bj;
   return 0;
@@ -576,7 +575,10 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     if (use_chunks) {
       const int q = (int)std::max<long long>(16, (level_kb + kWarpSlots - 1) / kWarpSlots);
       split_kb = std::min(kSplitK / 4, std::max(32, 4 * q));
-      chunk_kb = std::max(kChunkMinKB, (8 * q + 7) & ~7);
+      // a slice = one CTA slot's share of the level (8 q).  Smaller slices, i.e. several waves of CTAs per level, are
+      // slower: 0.875 / 0.917 / 0.958 ms for the apply of one 64^3 block with 8 q / 4 q / 2 q (more partial sums to combine)
+      const int per_unit = getenv("PREALPS_BJ_CHUNKQ") ? atoi(getenv("PREALPS_BJ_CHUNKQ")) : 8;
+      chunk_kb = std::max(kChunkMinKB, (per_unit * q + 7) & ~7);
     }
     int nlong = 0;
     while (nlong < count && klen_of[first + nlong] / 4 >= split_kb) ++nlong;
@@ -613,7 +615,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     std::vector<int> kl;
     for (auto& e : lst) {
       const int s = e.second.first, p = e.second.second;
-      FwdPanel P{fdoubles, uoff[s], e.first, sn_c0[s], 32 * p, sn_w[s], sn_h[s], -1, 0, -1, 0, 0};  // dependencies: below
+      FwdPanel P{fdoubles, uoff[s], e.first, sn_c0[s], 32 * p, sn_w[s], sn_h[s], 0};
       pk_f[l].push_back({zoff[s], fdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
       fdoubles += (long long)e.first * 32;
       bj->fwd_lvl_bytes[l] += 8.0 * e.first * 32;
@@ -639,7 +641,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     const int b0 = (int)bp.size();
     for (auto& e : lst) {
       const int s = e.second.first, p = e.second.second;
-      BwdPanel P{bdoubles, sn_rp[s], e.first, 32 * p, sn_c0[s], sn_w[s], sn_h[s], -1, 0, -1, 0, 0};
+      BwdPanel P{bdoubles, sn_rp[s], e.first, 32 * p, sn_c0[s], sn_w[s], sn_h[s], 0};
       pk_b[l].push_back({zoff[s], bdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
       bdoubles += (long long)e.first * 32;
       bj->bwd_lvl_bytes[l] += 8.0 * e.first * 32;
@@ -670,91 +672,15 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     for (int i = sn_w[s]; i < sn_h[s]; ++i) gl_ptr[rows[sn_rp[s] + i] + 1]++;
   for (int c = 0; c < n; ++c) gl_ptr[c + 1] += gl_ptr[c];
   {
+    bj->lvl_long_lists.assign(nlev, 0);
+    for (int l = 0; l < nlev; ++l) {
+      long long ent = 0;
+      for (int q = bj->lvl_col_ptr[l]; q < bj->lvl_col_ptr[l + 1]; ++q) ent += gl_ptr[lvl_cols[q] + 1] - gl_ptr[lvl_cols[q]];
+      bj->lvl_long_lists[l] = ent > 16ll * std::max(1, bj->lvl_col_ptr[l + 1] - bj->lvl_col_ptr[l]);
+    }
     std::vector<long long> fill(gl_ptr.begin(), gl_ptr.end() - 1);
     for (int s = 0; s < ns; ++s)  // ascending supernode order => fixed summation order
       for (int i = sn_w[s]; i < sn_h[s]; ++i) gl_idx[fill[rows[sn_rp[s] + i]]++] = uoff[s] + (i - sn_w[s]);
-  }
-  // ---- dataflow apply: dependencies of every panel, assembly tasks, and ALL work units of one apply in ticket order.
-  // A unit only ever waits for units with a smaller ticket (assembly before the panels of its level, children one level
-  // below their parent, the backward sweep after the forward one), so the CTA that draws a ticket always finds its
-  // predecessors finished or running.
-  std::vector<WorkUnit> all;
-  std::vector<AsmTask> atasks;
-  {
-    auto nfwd = [&](int s) { return (sn_h[s] + 31) / 32; };
-    auto nbwd = [&](int s) { return (sn_w[s] + 31) / 32; };
-    std::vector<int> ftarget(ns, 0), natasks(ns, 0);
-    for (int s = 0; s < ns; ++s) if (sn_par[s] >= 0) ftarget[sn_par[s]] += nfwd(s);
-    // assembly tasks: a warp handles 8 columns at a time (t = 8) and walks a column's gather list 8 entries per round trip;
-    // a task is a run of such passes whose chain of dependent round trips stays short -- the few thousand columns at the top
-    // of the forest, with hundreds of update rows each, spread over the whole machine like one column per lane group
-    std::vector<std::vector<AsmTask>> sn_tasks(ns);
-    for (int s = 0; s < ns; ++s) {
-      if (nchild[s] == 0) continue;
-      int begin = 0, cost = 0;
-      for (int c = 0; c < sn_w[s]; c += 8) {
-        long long maxlen = 0;
-        for (int j = c; j < std::min(sn_w[s], c + 8); ++j) maxlen = std::max(maxlen, gl_ptr[sn_c0[s] + j + 1] - gl_ptr[sn_c0[s] + j]);
-        const int pc = 1 + (int)((maxlen + 7) / 8);
-        if (c > begin && (cost + pc > kAsmChain || c - begin >= kAsmCols)) {
-          sn_tasks[s].push_back({sn_c0[s] + begin, sn_c0[s] + c, 4 * s + 0, 0, 4 * s + 1, {0, 0, 0}});
-          begin = c; cost = 0;
-        }
-        cost += pc;
-      }
-      sn_tasks[s].push_back({sn_c0[s] + begin, sn_c0[s] + sn_w[s], 4 * s + 0, 0, 4 * s + 1, {0, 0, 0}});
-      natasks[s] = (int)sn_tasks[s].size();
-    }
-    for (size_t i = 0; i < fp.size(); ++i) {
-      const int s = fp_sn[i];
-      if (nchild[s] > 0) { fp[i].dep = 4 * s + 1; fp[i].dep_target = natasks[s]; }
-      else fp[i].flags = 1;
-      fp[i].sig = sn_par[s] >= 0 ? 4 * sn_par[s] + 0 : 4 * s + 3;
-    }
-    for (size_t i = 0; i < bp.size(); ++i) {
-      const int s = bp_sn[i], par = sn_par[s];
-      bp[i].dep = par >= 0 ? 4 * par + 2 : 4 * s + 3;
-      bp[i].dep_target = par >= 0 ? nbwd(par) : nfwd(s);
-      bp[i].sig = 4 * s + 2;
-    }
-    int slot_base = 0, ctr_base = 0;
-    auto add_units = [&](const std::vector<WorkUnit>& src, int u0, int u1, int type) {
-      int slots = 0, ctrs = 0;
-      for (int i = u0; i < u1; ++i) {
-        WorkUnit u = src[i];
-        u.type = type;
-        if (u.split == 2) {
-          slots = std::max(slots, u.slot + u.nchunks);
-          ctrs = std::max(ctrs, u.cidx + 1);
-          u.slot += slot_base;
-          u.cidx += ctr_base;
-        }
-        all.push_back(u);
-      }
-      slot_base += slots;
-      ctr_base += ctrs;
-    };
-    auto add_tiny = [&](int first, int count, int type) {
-      for (int i = 0; i < count; i += kTinyUnit) all.push_back({first + i, std::min(kTinyUnit, count - i), 0, 0, 0, 0, 1, 0, 0, type});
-    };
-    for (int l = 0; l < nlev; ++l) {
-      const int t0 = (int)atasks.size();
-      for (int q = lev_ptr[l]; q < lev_ptr[l + 1]; ++q) {
-        const int s = order[q];
-        for (AsmTask tk : sn_tasks[s]) { tk.dep_target = ftarget[s]; atasks.push_back(tk); }
-      }
-      for (int i = t0; i < (int)atasks.size(); i += 8) all.push_back({i, std::min(8, (int)atasks.size() - i), 0, 0, 0, 0, 1, 0, 0, kUnitAsm});
-      add_units(fu, bj->fwd_unit_ptr[l], bj->fwd_unit_ptr[l + 1], kUnitFwd);
-      add_tiny(bj->fwd_tiny0[l], bj->fwd_tinyn[l], kUnitFwdTiny);
-    }
-    for (int l = nlev - 1; l >= 0; --l) {
-      add_units(bu, bj->bwd_unit_ptr[l], bj->bwd_unit_ptr[l + 1], kUnitBwd);
-      add_tiny(bj->bwd_tiny0[l], bj->bwd_tinyn[l], kUnitBwdTiny);
-    }
-    bj->all_slots = slot_base;
-    bj->all_counters = ctr_base;
-    bj->n_all_units = (int)all.size();
-    bj->dep_ints = 4ll * ns + 8;
   }
   bj->stat[7] = now_s() - t_an0;
 
@@ -783,8 +709,6 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       upload(&bj->bwd_units, bu) || upload(&bj->perm, perm) || upload(&bj->rows, rows) ||
       upload(&bj->lvl_cols, lvl_cols) || upload(&bj->gl_ptr, gl_ptr) || upload(&bj->gl_idx, gl_idx))
     return 1;
-  if (upload(&bj->all_units, all) || upload(&bj->asm_tasks, atasks)) return 1;
-  PCU_CUDA(cudaMalloc(&bj->dep, sizeof(int) * (size_t)bj->dep_ints));
 
   // ---------------------------------------------------------------- numeric factorisation
   cudaStream_t st = ctx->stream;
@@ -943,14 +867,22 @@ int pcu_bj_analyze(int n, const int* rowPtr, const int* colInd, int use_metis, i
 
 double pcu_bj_stat(pcu_bj* bj, int which) {
   if (!bj || which < 0 || which >= 16) return -1.0;
-  if (which == 4) return pcu_bj_bytes(bj, 8);
+  if (which == 4) return pcu_bj_stored_bytes(bj, 8);
   return bj->stat[which];
 }
 
 double pcu_bj_bytes(pcu_bj* bj, int t) {
-  // SURVEY.md 8(d), dense-supernode form: both copies of the factor streamed once
-  // (8 B per stored entry), the panel descriptors, and the block vectors:
-  // read B, write/read Wk and Y once each, write X, write+read the update rows.
+  // SURVEY.md 8(d), dense-supernode form (8 B per non-zero of L, no index per entry): L streamed once forward and once
+  // backward -- the EXACT non-zeros of the factor, relaxation zeros and panel padding not counted -- plus one pointer
+  // per row and sweep, plus read + write of the m x t block in each sweep
+  const double vec = (double)bj->n * t * 8.0;
+  return 2.0 * (8.0 * bj->stat[0] + 8.0 * ((double)bj->n + bj->nblk)) + 4.0 * vec;
+}
+
+double pcu_bj_stored_bytes(pcu_bj* bj, int t) {
+  // what the kernels have to move: both copies of the stored panels (explicit zeros of the relaxed supernodes and the
+  // padding of the 32-row panels included), the block vectors (read B, write/read Wk and Y once each, write X) and
+  // the update rows (written by the forward sweep, gathered by the assembly)
   const double vec = (double)bj->n * t * 8.0;
   return 8.0 * ((double)bj->fwd_doubles + (double)bj->bwd_doubles) + 6.0 * vec +
          2.0 * (double)bj->nu * t * 8.0 + (double)bj->nu * 8.0;

@@ -37,19 +37,26 @@ inline void pdl_wait() {}
 inline void pdl_launch_dependents() {}
 #endif
 
-// ---- forward right-hand-side assembly: one group of G lanes per column
-// PREFETCH (opt-in, PREALPS_BJ_ASM_PREFETCH=1; written after the last GPU session of round 1, not measured yet): a
-// group's FIRST column fetches everything static -- its forest column, the row of the caller's block it maps to, its
-// gather range and the first 8 gather indices -- BEFORE griddepcontrol.wait, i.e. while the previous level's forward
-// sweep drains; only the loads of B and U (data written earlier in the stream) come after the wait.  An assemble launch
-// above level 0 moves ~10 MB and is a chain of 4 dependent round trips; this takes 3 of them off the critical path.
-template <int T, bool PREFETCH>
-__global__ void __launch_bounds__(kThreads) assemble_kernel(const int* __restrict__ cols, int ncols,
-                                                            const double* __restrict__ B, int ldb, int t,
-                                                            const int* __restrict__ perm,
-                                                            const long long* __restrict__ gl_ptr,
-                                                            const long long* __restrict__ gl_idx,
-                                                            const double* __restrict__ U, double* __restrict__ Wk) {
+// ---- forward right-hand-side assembly: one group of G lanes per column.
+// A group's FIRST column fetches everything static -- its forest column, the row of the caller's block it maps to, its
+// gather range and the first gather indices -- BEFORE griddepcontrol.wait, i.e. while the previous level's forward sweep
+// drains; only the loads of B and U (data written earlier in the stream) come after the wait (measured: 0.941 -> 0.923 ms
+// for the apply of one 64^3 block).
+// The list is walked in order (fixed summation order), NB update rows in flight per lane group; the indices of the next
+// batch are fetched while the rows of the current one are in flight.  NB = 16 for the levels whose columns gather
+// hundreds of update rows (the top of the forest: an assembly launch there is one chain of dependent round trips, its
+// length is what the launch costs), NB = 8 (fewer registers, more resident warps) where the lists are short or empty.
+// Slots past the end of a list point at row `pad` of U, which is zero and never written: the loads of a batch carry no
+// predicate, and with the minimum-CTAs launch bound ptxas issues them back to back instead of sinking each next to its
+// subtraction (x - 0.0 == x: the padding does not change a bit).
+template <int T, int NB>
+__global__ void __launch_bounds__(kThreads, NB == 16 ? 2 : 4) assemble_kernel(const int* __restrict__ cols, int ncols,
+                                                                              const double* __restrict__ B, int ldb, int t,
+                                                                              const int* __restrict__ perm,
+                                                                              const long long* __restrict__ gl_ptr,
+                                                                              const long long* __restrict__ gl_idx,
+                                                                              const double* __restrict__ U, long long pad,
+                                                                              double* __restrict__ Wk) {
   constexpr int CPL = (T >= 2) ? 2 : 1;
   constexpr int G = T / CPL;
   const int gid = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) / G);
@@ -57,44 +64,43 @@ __global__ void __launch_bounds__(kThreads) assemble_kernel(const int* __restric
   const int ngroups = (int)((long long)gridDim.x * blockDim.x / G);
   int c_first = 0, row_first = 0;
   long long g_first = 0, g1_first = 0;
-  long long idx_first[8];
-  if (PREFETCH && gid < ncols) {
+  long long idx[NB];
+  if (gid < ncols) {
     c_first = __ldg(cols + gid);
     row_first = __ldg(perm + c_first);
     g_first = __ldg(gl_ptr + c_first);
     g1_first = __ldg(gl_ptr + c_first + 1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) idx_first[j] = (g_first + j < g1_first) ? __ldg(gl_idx + g_first + j) : -1;
+    for (int j = 0; j < NB; ++j) idx[j] = (g_first + j < g1_first) ? __ldg(gl_idx + g_first + j) : pad;
   }
   pdl_wait();
   pdl_launch_dependents();
   for (int q = gid; q < ncols; q += ngroups) {
-    const bool pre = PREFETCH && q == gid;
+    const bool pre = (q == gid);
     const int c = pre ? c_first : cols[q];
     const double* src = B + (size_t)(pre ? row_first : perm[c]) * ldb;
     double a0 = 0.0, a1 = 0.0;
     const int c0 = CPL * lig;
     if (c0 < t) a0 = src[c0];
     if (CPL == 2 && c0 + 1 < t) a1 = src[c0 + 1];
-    // the list is walked in order (fixed summation order); 8 slots are fetched at a time so the loads overlap
     const long long g0 = pre ? g_first : gl_ptr[c];
     const long long g1 = pre ? g1_first : gl_ptr[c + 1];
-    for (long long g = g0; g < g1; g += 8) {
-      long long idx[8];
-      double2 v[8];
+    if (!pre) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) idx[j] = (pre && g == g0) ? idx_first[j] : ((g + j < g1) ? __ldg(gl_idx + g + j) : -1);
+      for (int j = 0; j < NB; ++j) idx[j] = (g0 + j < g1) ? __ldg(gl_idx + g0 + j) : pad;
+    }
+    for (long long g = g0; g < g1; g += NB) {
+      double2 v[NB];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = make_double2(0.0, 0.0);
-        if (idx[j] >= 0) {
-          const double* u = U + (size_t)idx[j] * T + c0;
-          if (CPL == 2) v[j] = *reinterpret_cast<const double2*>(u);
-          else v[j].x = u[0];
-        }
+      for (int j = 0; j < NB; ++j) {
+        const double* u = U + (size_t)idx[j] * T + c0;
+        if (CPL == 2) v[j] = *reinterpret_cast<const double2*>(u);
+        else v[j] = make_double2(u[0], 0.0);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a0 -= v[j].x; a1 -= v[j].y; }
+      for (int j = 0; j < NB; ++j) idx[j] = (g + NB + j < g1) ? __ldg(gl_idx + g + NB + j) : pad;  // next batch
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { a0 -= v[j].x; a1 -= v[j].y; }
     }
     double* dst = Wk + (size_t)c * T + c0;
     if (CPL == 2) *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
@@ -186,8 +192,8 @@ inline void dmma884(double& d0, double& d1, double a, double b) {
 #endif
 
 // lane owns, for every row group rg and column block nb: row row0 + 8*rg + lane/4, columns 8*nb + 2*(lane%4) + {0,1}
-template <int T, bool FWD, class Args>
-__device__ __forceinline__ void store_outputs(const double (&acc)[4][(T + 7) / 8][2], const Args& a, int row0, int c0,
+template <int T, bool FWD>
+__device__ __forceinline__ void store_outputs(const double (&acc)[4][(T + 7) / 8][2], const SweepArgs& a, int row0, int c0,
                                               int w, int h, long long uoff, int lr, int lk) {
   constexpr int NB = (T + 7) / 8;
 #pragma unroll
@@ -482,491 +488,6 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
   store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
 }
 
-// ================================================================ dataflow apply: ONE persistent launch per apply
-// Level-by-level launches leave the machine idle at every level boundary (the tail of a level, then the latency chain of
-// the next level's first loads) and pay an assembly launch of pure latency per level: with one 64^3 subdomain per GPU
-// that is more than half of the apply (0.94 ms for 2.4 GB).  Here the apply is one launch of resident CTAs that draw work
-// units from a ticket counter -- assembly tasks, forward panels, backward panels, ordered so that a unit only ever waits
-// for units with a smaller ticket -- and a unit starts as soon as the supernodes it depends on have signalled (bj.h: four
-// counters per supernode), whatever level the rest of the forest is at.  Operation order inside a panel and inside a
-// gather list is the one of the per-level kernels: same bits.
-// Memory model: a producer stores its outputs, __syncwarp / __syncthreads, one thread fences (cumulative) and increments
-// the counter; consumers poll it with ld.acquire.gpu and read what was produced inside this launch through L2 only
-// (cp.async.cg, ld.global.cg) -- an L1 line fetched earlier for a neighbouring row could hold a stale copy.
-struct DfArgs {
-  const WorkUnit* units;
-  int nunits;
-  const FwdPanel* fpan;
-  const BwdPanel* bpan;
-  const AsmTask* atasks;
-  const double* fdata;
-  const double* bdata;
-  const double* B;      // the caller's block: forward input
-  int ldb;
-  int b_vec;            // rows of B are 16-byte aligned: leaf panels fetch them with cp.async
-  double* Wk;
-  double* Y;
-  double* U;
-  double* Xp;
-  const int* rows;
-  const int* perm;
-  const long long* gl_ptr;
-  const long long* gl_idx;
-  double* Out;
-  int ldo;
-  int t;
-  double* scratch;
-  int* counters;
-  int* dep;             // 4 counters per supernode
-  int* ticket;
-  long long* prof;      // PREALPS_BJ_DFPROF=1: per unit type {units, cycles, cycles spent waiting}, else nullptr
-};
-
-#ifndef PCU_EMUL
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ int draw_ticket(int* p) {
-  int v;
-  asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double2 ld_cg2(const double* p) {
-  double2 v;
-  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-  return v;
-}
-// 16-byte cp.async that reads only the first src_bytes (0, 8 or 16) and zero-fills the rest
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
-constexpr long long kSpinLimit = 1ll << 34;  // ~9 s of SM clocks: a dependency that never arrives traps instead of hanging
-// ONE lane polls (every lane of every waiting warp polling the same counter made that L2 slice the bottleneck of the
-// whole apply: signals queued behind the polls), with a back-off that keeps a few hundred waiters below the slice's rate
-__device__ __forceinline__ void df_poll(const int* p, int target) {
-  if (ld_acquire_gpu(p) >= target) return;
-  const long long t0 = clock64();
-  unsigned ns = 64;
-  while (ld_acquire_gpu(p) < target) {
-    __nanosleep(ns);
-    if (ns < 1024) ns <<= 1;
-    if (clock64() - t0 > kSpinLimit) __trap();
-  }
-}
-// the calling warp waits (its lanes may be about to read what the dependency produced)
-__device__ __forceinline__ void df_wait(const int* dep, int idx, int target) {
-  if (idx < 0 || target <= 0) return;
-  if ((threadIdx.x & 31) == 0) df_poll(dep + idx, target);
-  __syncwarp();
-}
-#else  // tests/emul runs the CTAs one after the other: the first one draws every ticket, in order
-inline int ld_acquire_gpu(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
-inline int draw_ticket(int* p) { return __atomic_fetch_add(p, 1, __ATOMIC_SEQ_CST); }
-inline double2 ld_cg2(const double* p) { pcu_emul_check_aligned(p, 16); return make_double2(p[0], p[1]); }
-inline void cp_async16_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
-  pcu_emul_check_aligned(smem_dst, 16);
-  pcu_emul_check_aligned(gmem_src, 16);
-  std::memset(smem_dst, 0, 16);
-  if (src_bytes > 0) std::memcpy(smem_dst, gmem_src, (size_t)src_bytes);
-}
-inline void df_wait(const int* dep, int idx, int target) {
-  if (idx < 0 || target <= 0) return;
-  if (ld_acquire_gpu(dep + idx) < target) {  // units run in ticket order here: an unmet dependency is an ordering bug
-    std::fprintf(stderr, "[emul] dataflow apply: counter %d is %d, unit needs %d\n", idx, dep[idx], target);
-    std::abort();
-  }
-}
-#endif
-
-// by ONE thread, after the barrier that follows the stores of everyone who produced the data
-__device__ __forceinline__ void df_signal(int* dep, int idx) {
-  if (idx < 0) return;
-  __threadfence();
-  atomicAdd(dep + idx, 1);
-}
-
-// input rows of a forward panel without children: B[perm[c]] straight from the caller's block, columns >= t as zeros
-template <int T>
-__device__ __forceinline__ void stage_direct_row(const DfArgs& a, int c, int part, double* dst) {
-  const double* row = a.B + (size_t)__ldg(a.perm + c) * a.ldb;
-  if (T >= 2) {
-    const int nv = min(2, max(0, a.t - 2 * part));
-    if (a.b_vec) cp_async16_zfill(dst, nv > 0 ? row + 2 * part : row, 8 * nv);
-    else {
-      dst[0] = (nv > 0) ? row[2 * part] : 0.0;
-      dst[1] = (nv > 1) ? row[2 * part + 1] : 0.0;
-    }
-  } else {
-    dst[0] = row[0];
-  }
-}
-
-// sweep_kernel as a work unit: one warp per panel, or the 8 warps on one panel (or on one slice of it)
-template <int T, bool FWD>
-__device__ __forceinline__ void df_sweep_unit(const DfArgs& a, const WorkUnit& u, double* smem) {
-  constexpr int D = 4;
-  constexpr int NB = (T + 7) / 8;
-  constexpr int KT = Tile<T>::KT;
-  constexpr int KB = KT / 4;
-  constexpr int TILE = KT * T;
-  double* red = smem;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lr = lane >> 2, lk = lane & 3;
-  double* tile0 = smem + 32 * T + (size_t)warp * 2 * TILE;
-  if (!u.split && warp >= u.count) return;
-  const int pidx = u.split ? u.first : u.first + warp;
-  long long off;
-  int klen, c0, w, h, row0, dep, dep_target, sig;
-  long long uoff = 0, rows_off = 0;
-  bool direct = false;
-  if (FWD) {
-    const FwdPanel p = a.fpan[pidx];
-    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.row0; uoff = p.uoff;
-    dep = p.dep; dep_target = p.dep_target; sig = p.sig; direct = (p.flags & 1) != 0;
-  } else {
-    const BwdPanel p = a.bpan[pidx];
-    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
-    dep = p.dep; dep_target = p.dep_target; sig = p.sig;
-  }
-  const int nkb = klen >> 2;
-  int q0 = 0, q1 = nkb;
-  if (u.split) {
-    const int s0 = (u.split == 2) ? u.kb0 : 0, s1 = (u.split == 2) ? u.kb1 : nkb;
-    int per = (s1 - s0 + kWarps - 1) / kWarps;
-    per = (per + KB - 1) / KB * KB;
-    q0 = min(s1, s0 + warp * per);
-    q1 = min(s1, q0 + per);
-  }
-  double acc[4][NB][2];
-#pragma unroll
-  for (int rg = 0; rg < 4; ++rg)
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
-  const double* base = (FWD ? a.fdata : a.bdata) + off + lane * 4;
-  const int* rows = a.rows + rows_off;
-
-  auto stage = [&](int tq, double* buf) {
-    constexpr int CHUNKS = (T >= 2) ? TILE / 2 : KT;
-    constexpr int CPR = (T >= 2) ? T / 2 : 1;
-#pragma unroll
-    for (int c0q = 0; c0q < CHUNKS; c0q += 32) {
-      const int q = c0q + lane;
-      if (T >= 2) {
-        const int r = q / CPR, part = q % CPR;
-        const int k = min(4 * tq + r, klen - 1);
-        if (FWD && direct) { stage_direct_row<T>(a, c0 + k, part, buf + (size_t)r * T + 2 * part); continue; }
-        const double* src;
-        if (FWD) src = a.Wk + (size_t)(c0 + k) * T;
-        else {
-          const int i = min(row0 + k, h - 1);
-          src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
-        }
-        cp_async16(buf + (size_t)r * T + 2 * part, src + 2 * part);
-      } else if (q < KT) {
-        const int k = min(4 * tq + q, klen - 1);
-        if (FWD && direct) { stage_direct_row<T>(a, c0 + k, 0, buf + q); continue; }
-        const double* src;
-        if (FWD) src = a.Wk + (size_t)(c0 + k);
-        else { const int i = min(row0 + k, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
-        buf[q] = __ldcg(src);
-      }
-    }
-    cp_async_commit();
-  };
-
-  double2 ring0[D], ring1[D];
-  auto issue = [&](int kb, double2& m0, double2& m1) {
-    if (kb < q1) ld_stream4(base + (size_t)kb * 128, m0, m1);
-    else { m0 = make_double2(0.0, 0.0); m1 = m0; }
-  };
-  // the panel itself is static: in flight before the dependency is checked
-  if (q0 < q1) {
-#pragma unroll
-    for (int u2 = 0; u2 < D; ++u2) issue(q0 + u2, ring0[u2], ring1[u2]);
-  }
-  {
-    long long tw0 = 0;
-    if (a.prof && lane == 0) tw0 = clock64();
-    df_wait(a.dep, dep, dep_target);
-    if (a.prof && lane == 0 && (warp == 0 || !u.split))
-      atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + 3 * (FWD ? kUnitFwd : kUnitBwd) + 2, (unsigned long long)(clock64() - tw0));
-  }
-  if (q0 < q1) {
-    stage(q0, tile0);
-    int tix = 0;
-    for (int tq = q0; tq < q1; tq += KB, ++tix) {
-      const double* cur = tile0 + (size_t)(tix & 1) * TILE;
-      if (tq + KB < q1) { stage(tq + KB, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
-      __syncwarp();
-#pragma unroll 1
-      for (int kq = 0; kq < KB; kq += D) {
-#pragma unroll
-        for (int u2 = 0; u2 < D; ++u2) {
-          const double2 m0 = ring0[u2], m1 = ring1[u2];
-          issue(tq + kq + u2 + D, ring0[u2], ring1[u2]);
-          const double* brow = cur + (size_t)(4 * (kq + u2) + lk) * T;
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
-            dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
-            dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
-            dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
-            dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-  if (u.split) {
-#pragma unroll
-    for (int rg = 0; rg < 4; ++rg)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = 8 * nb + 2 * lk + e;
-          if (col < T) tile0[(8 * rg + lr) * T + col] = acc[rg][nb][e];
-        }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 32 * T; e += kThreads) {
-      double sum = smem[32 * T + e];
-#pragma unroll
-      for (int wv = 1; wv < kWarps; ++wv) sum += smem[32 * T + (size_t)wv * 2 * TILE + e];
-      red[e] = sum;
-    }
-    __syncthreads();
-    if (warp != 0) return;
-    if (u.split == 2) {
-      double* mine = a.scratch + (size_t)(u.slot + u.chunk) * 32 * T;
-      for (int e = lane; e < 32 * T; e += 32) mine[e] = red[e];
-      __threadfence();
-      int last = 0;
-      if (lane == 0) last = (atomicAdd(a.counters + u.cidx, 1) == u.nchunks - 1);
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (!last) return;
-      __threadfence();
-      if (lane == 0) a.counters[u.cidx] = 0;
-      for (int e = lane; e < 32 * T; e += 32) {
-        double sacc = 0.0;
-        for (int ch = 0; ch < u.nchunks; ++ch) sacc += __ldcg(a.scratch + (size_t)(u.slot + ch) * 32 * T + e);
-        red[e] = sacc;
-      }
-      __syncwarp();
-    }
-#pragma unroll
-    for (int rg = 0; rg < 4; ++rg)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = 8 * nb + 2 * lk + e;
-          if (col < T) acc[rg][nb][e] = red[(8 * rg + lr) * T + col];
-        }
-  }
-  store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
-  if (u.split == 2) {  // only the CTA that arrived last knows that the panel is complete: it signals itself
-    __syncwarp();
-    if (lane == 0) df_signal(a.dep, sig);
-  }
-}
-
-// tiny panels (klen <= kTinyK): TW warps, each takes panels first + warp, first + warp + TW, ... and stages a whole panel
-// and its input rows into its own shared-memory slab with cp.async (sweep_tiny_kernel as a work unit)
-template <int T>
-struct TinyWarps { static constexpr int TW = (T <= 16) ? 8 : 5; };
-
-template <int T, bool FWD>
-__device__ __forceinline__ void df_tiny_unit(const DfArgs& a, const WorkUnit& u, double* smem) {
-  constexpr int NB = (T + 7) / 8;
-  constexpr int KMAX = kTinyK;
-  constexpr int MB = KMAX * 32, BB = KMAX * T;
-  constexpr int TW = TinyWarps<T>::TW;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lr = lane >> 2, lk = lane & 3;
-  if (warp >= TW) return;
-  double* mbuf = smem + (size_t)warp * (MB + BB);
-  double* bbuf = mbuf + MB;
-  const unsigned long long pol = l2_evict_first_policy();
-  for (int q = warp; q < u.count; q += TW) {
-    long long off;
-    int klen, c0, w, h, row0, dep, dep_target;
-    long long uoff = 0, rows_off = 0;
-    bool direct = false;
-    if (FWD) {
-      const FwdPanel p = a.fpan[u.first + q];
-      off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.row0; uoff = p.uoff;
-      dep = p.dep; dep_target = p.dep_target; direct = (p.flags & 1) != 0;
-    } else {
-      const BwdPanel p = a.bpan[u.first + q];
-      off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
-      dep = p.dep; dep_target = p.dep_target;
-    }
-    const int nkb = klen >> 2;
-    const double* base = (FWD ? a.fdata : a.bdata) + off + lane * 4;
-    const int* rows = a.rows + rows_off;
-    for (int kb = 0; kb < nkb; ++kb) {
-      cp_async16_stream(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128, pol);
-      cp_async16_stream(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2, pol);
-    }
-    {  // the panel itself is static; its input rows are what the dependency produces
-      long long tw0 = 0;
-      if (a.prof && lane == 0) tw0 = clock64();
-      df_wait(a.dep, dep, dep_target);
-      if (a.prof && lane == 0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + 3 * (FWD ? kUnitFwdTiny : kUnitBwdTiny) + 2, (unsigned long long)(clock64() - tw0));
-    }
-    if (T >= 2) {
-      constexpr int CPR = (T >= 2) ? T / 2 : 1;
-      const int chunks = klen * CPR;
-      for (int qq = lane; qq < chunks; qq += 32) {
-        const int r = qq / CPR, part = qq % CPR;
-        if (FWD && direct) { stage_direct_row<T>(a, c0 + r, part, bbuf + (size_t)r * T + 2 * part); continue; }
-        const double* src;
-        if (FWD) src = a.Wk + (size_t)(c0 + r) * T;
-        else {
-          const int i = min(row0 + r, h - 1);
-          src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
-        }
-        cp_async16(bbuf + (size_t)r * T + 2 * part, src + 2 * part);
-      }
-    } else {
-      for (int r = lane; r < klen; r += 32) {
-        if (FWD && direct) { stage_direct_row<T>(a, c0 + r, 0, bbuf + r); continue; }
-        const double* src;
-        if (FWD) src = a.Wk + (size_t)(c0 + r);
-        else { const int i = min(row0 + r, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
-        bbuf[r] = __ldcg(src);
-      }
-    }
-    cp_async_commit();
-    double acc[4][NB][2];
-#pragma unroll
-    for (int rg = 0; rg < 4; ++rg)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
-    cp_async_wait<0>();
-    __syncwarp();
-#pragma unroll 2
-    for (int kb = 0; kb < nkb; ++kb) {
-      const double2 m0 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4);
-      const double2 m1 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4 + 2);
-      const double* brow = bbuf + (size_t)(4 * kb + lk) * T;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
-        dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
-        dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
-        dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
-        dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
-      }
-    }
-    store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
-    __syncwarp();  // every lane is done with the slab that the next panel overwrites
-  }
-}
-
-// forward right-hand side of up to 8 column ranges, one per warp (assemble_kernel as a work unit)
-template <int T>
-__device__ __forceinline__ void df_asm_unit(const DfArgs& a, const WorkUnit& u) {
-  constexpr int CPL = (T >= 2) ? 2 : 1;
-  constexpr int G = T / CPL;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= u.count) return;
-  const AsmTask tk = a.atasks[u.first + warp];
-  {
-    long long tw0 = 0;
-    if (a.prof && lane == 0) tw0 = clock64();
-    df_wait(a.dep, tk.dep, tk.dep_target);
-    if (a.prof && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + 3 * kUnitAsm + 2, (unsigned long long)(clock64() - tw0));
-  }
-  const int grp = lane / G, lig = lane % G;
-  const int c0 = CPL * lig;
-  for (int c = tk.c_begin + grp; c < tk.c_end; c += 32 / G) {
-    const double* src = a.B + (size_t)__ldg(a.perm + c) * a.ldb;
-    double a0 = 0.0, a1 = 0.0;
-    if (c0 < a.t) a0 = src[c0];
-    if (CPL == 2 && c0 + 1 < a.t) a1 = src[c0 + 1];
-    const long long g1 = __ldg(a.gl_ptr + c + 1);
-    for (long long g = __ldg(a.gl_ptr + c); g < g1; g += 8) {  // in list order, 8 loads in flight
-      long long idx[8];
-      double2 v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) idx[j] = (g + j < g1) ? __ldg(a.gl_idx + g + j) : -1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = make_double2(0.0, 0.0);
-        if (idx[j] >= 0) {
-          const double* up = a.U + (size_t)idx[j] * T + c0;
-          if (CPL == 2) v[j] = ld_cg2(up);
-          else v[j].x = __ldcg(up);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { a0 -= v[j].x; a1 -= v[j].y; }
-    }
-    double* dst = a.Wk + (size_t)c * T + c0;
-    if (CPL == 2) *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
-    else dst[0] = a0;
-  }
-}
-
-template <int T>
-struct DfSmem {
-  static constexpr int sweep = (32 * T + kWarps * 2 * Tile<T>::KT * T) * (int)sizeof(double);
-  static constexpr int tiny = TinyWarps<T>::TW * (kTinyK * 32 + kTinyK * T) * (int)sizeof(double);
-  static constexpr int bytes = sweep > tiny ? sweep : tiny;
-};
-
-template <int T>
-__global__ void __launch_bounds__(kThreads, 2) apply_kernel(DfArgs a) {
-  PCU_DYN_SMEM(smem);
-  __shared__ int s_next;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_next = draw_ticket(a.ticket);
-  __syncthreads();
-  int ui = s_next;
-  while (ui < a.nunits) {
-    __syncthreads();  // everyone has read s_next
-    int nxt = 0;
-    if (tid == 0) nxt = draw_ticket(a.ticket);  // the next ticket is drawn while this unit runs
-    const WorkUnit u = a.units[ui];
-    long long tp0 = 0;
-    if (a.prof && tid == 0) tp0 = clock64();
-    switch (u.type) {
-      case kUnitAsm: df_asm_unit<T>(a, u); break;
-      case kUnitFwd: df_sweep_unit<T, true>(a, u, smem); break;
-      case kUnitFwdTiny: df_tiny_unit<T, true>(a, u, smem); break;
-      case kUnitBwd: df_sweep_unit<T, false>(a, u, smem); break;
-      default: df_tiny_unit<T, false>(a, u, smem); break;
-    }
-    if (tid == 0) s_next = nxt;
-    __syncthreads();  // every output of the unit is stored, its shared memory is free again, s_next is published
-    // one fence for the whole unit, then one increment per finished panel / task (a panel cut across CTAs was signalled
-    // by the CTA that arrived last)
-    if (tid < 32 && u.split != 2) {
-      const int np = u.split ? 1 : u.count;
-      int sig = -1;
-      if (tid < np) {
-        if (u.type == kUnitAsm) sig = a.atasks[u.first + tid].sig;
-        else if (u.type == kUnitFwd || u.type == kUnitFwdTiny) sig = a.fpan[u.first + tid].sig;
-        else sig = a.bpan[u.first + tid].sig;
-      }
-      __threadfence();
-      if (sig >= 0) atomicAdd(a.dep + sig, 1);
-    }
-    if (a.prof && tid == 0) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + 3 * u.type, 1ull);
-      atomicAdd(reinterpret_cast<unsigned long long*>(a.prof) + 3 * u.type + 1, (unsigned long long)(clock64() - tp0));
-    }
-    ui = s_next;
-  }
-}
-
 int pick_T(int t) { return t <= 1 ? 1 : t <= 2 ? 2 : t <= 4 ? 4 : t <= 8 ? 8 : t <= 16 ? 16 : 32; }
 
 int ensure_work(pcu_bj* bj, int T) {
@@ -977,9 +498,9 @@ int ensure_work(pcu_bj* bj, int T) {
   bj->Wk = bj->Y = bj->U = bj->Xp = nullptr;
   cudaFree(bj->scratch); cudaFree(bj->counters);
   bj->scratch = nullptr; bj->counters = nullptr;
-  PCU_CUDA(cudaMalloc(&bj->scratch, sizeof(double) * (size_t)(std::max(bj->scratch_slots, bj->all_slots) + 1) * 32 * T));
-  PCU_CUDA(cudaMalloc(&bj->counters, sizeof(int) * (size_t)(std::max(bj->ncounters, bj->all_counters) + 1)));
-  PCU_CUDA(cudaMemsetAsync(bj->counters, 0, sizeof(int) * (size_t)(std::max(bj->ncounters, bj->all_counters) + 1), c->stream));
+  PCU_CUDA(cudaMalloc(&bj->scratch, sizeof(double) * (size_t)(bj->scratch_slots + 1) * 32 * T));
+  PCU_CUDA(cudaMalloc(&bj->counters, sizeof(int) * (size_t)(bj->ncounters + 1)));
+  PCU_CUDA(cudaMemsetAsync(bj->counters, 0, sizeof(int) * (size_t)(bj->ncounters + 1), c->stream));
   const size_t nv = ((size_t)bj->n + 72) * T, nuv = ((size_t)bj->nu + 4) * T;
   PCU_CUDA(cudaMalloc(&bj->Wk, nv * sizeof(double)));
   PCU_CUDA(cudaMalloc(&bj->Y, nv * sizeof(double)));
@@ -1082,8 +603,10 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   pcu_ctx* c = bj->ctx;
   cudaStream_t st = c->stream;
   LevelProfiler prof(st);
-  const bool asm_prefetch = getenv("PREALPS_BJ_ASM_PREFETCH") != nullptr;  // read per apply: tests flip it in-process
   constexpr int G = (T >= 2) ? T / 2 : 1;
+  // the zero row behind the update rows: U holds (nu + 4) * cap_t doubles and a narrower solve uses the front of it, so the
+  // tail starts at row nu * cap_t / T of the T-wide layout whatever ran before
+  const long long pad = bj->nu * (long long)(bj->cap_t / T);
   SweepArgs a{};
   a.Wk = bj->Wk; a.Y = bj->Y; a.U = bj->U; a.Xp = bj->Xp; a.rows = bj->rows; a.perm = bj->perm;
   a.Out = X; a.ldo = ldx; a.t = t;
@@ -1093,12 +616,12 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
     if (ncols > 0) {
       prof.mark("asm L" + std::to_string(l) + " cols=" + std::to_string(ncols), 3.0 * ncols * T * 8);
       const int grid = stream_grid(c, (long long)ncols * G, kThreads, 8);
-      if (asm_prefetch)
-        launch_chain(assemble_kernel<T, true>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t,
-                     bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
+      if (bj->lvl_long_lists[l])
+        launch_chain(assemble_kernel<T, 16>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t,
+                     bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, pad, bj->Wk);
       else
-        launch_chain(assemble_kernel<T, false>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t,
-                     bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, bj->Wk);
+        launch_chain(assemble_kernel<T, 8>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t,
+                     bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, pad, bj->Wk);
       PCU_LAUNCH_CHECK(c);
     }
     const int nu = bj->fwd_unit_ptr[l + 1] - bj->fwd_unit_ptr[l];
@@ -1155,76 +678,11 @@ int dispatch_apply(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int
   }
 }
 
-template <int T>
-int dataflow_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
-  pcu_ctx* c = bj->ctx;
-  cudaStream_t st = c->stream;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    PCU_CUDA(cudaFuncSetAttribute(apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, DfSmem<T>::bytes));
-    int n = 0;
-    PCU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, apply_kernel<T>, kThreads, DfSmem<T>::bytes));
-    PCU_CHECK(n >= 1, "pcu_bj_apply: the apply kernel does not fit an SM at T = %d", T);
-    ctas_per_sm = n;
-  }
-  PCU_CUDA(cudaMemsetAsync(bj->dep, 0, sizeof(int) * (size_t)bj->dep_ints, st));
-  DfArgs a{};
-  a.units = bj->all_units; a.nunits = bj->n_all_units;
-  a.fpan = bj->fwd_panels; a.bpan = bj->bwd_panels; a.atasks = bj->asm_tasks;
-  a.fdata = bj->fwd_data; a.bdata = bj->bwd_data;
-  a.B = B; a.ldb = ldb;
-  a.b_vec = (T >= 2 && ldb % 2 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0) ? 1 : 0;
-  a.Wk = bj->Wk; a.Y = bj->Y; a.U = bj->U; a.Xp = bj->Xp; a.rows = bj->rows; a.perm = bj->perm;
-  a.gl_ptr = bj->gl_ptr; a.gl_idx = bj->gl_idx;
-  a.Out = X; a.ldo = ldx; a.t = t;
-  a.scratch = bj->scratch; a.counters = bj->counters;
-  a.dep = bj->dep; a.ticket = bj->dep + (bj->dep_ints - 8);
-  static long long* d_prof = nullptr;
-  const bool prof = getenv("PREALPS_BJ_DFPROF") != nullptr;
-  if (prof) {
-    if (!d_prof) PCU_CUDA(cudaMalloc(&d_prof, sizeof(long long) * 32));
-    PCU_CUDA(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 32, st));
-    a.prof = d_prof;
-  }
-  const int grid = std::max(1, std::min(bj->n_all_units, ctas_per_sm * c->num_sms));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)kThreads);
-  cfg.dynamicSmemBytes = DfSmem<T>::bytes;
-  cfg.stream = st;
-  cudaLaunchKernelEx(&cfg, apply_kernel<T>, a);
-  PCU_LAUNCH_CHECK(c);
-  if (prof) {  // cycles are summed over the CTAs (thread 0 of each): divide by grid x SM clock for a share of the apply
-    long long h[32];
-    PCU_CUDA(cudaStreamSynchronize(st));
-    PCU_CUDA(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
-    static const char* names[6] = {"-", "assemble", "fwd sweep", "fwd tiny", "bwd sweep", "bwd tiny"};
-    fprintf(stderr, "  dataflow apply, grid %d:", grid);
-    for (int k = 1; k < 6; ++k)
-      fprintf(stderr, "  %s: %lld units, %.1f Mcycles (waiting %.1f)", names[k], h[3 * k], h[3 * k + 1] * 1e-6, h[3 * k + 2] * 1e-6);
-    fprintf(stderr, "\n");
-  }
-  return 0;
-}
-
-int dispatch_dataflow(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
-  switch (pick_T(t)) {
-    case 1: return dataflow_T<1>(bj, B, ldb, X, ldx, t);
-    case 2: return dataflow_T<2>(bj, B, ldb, X, ldx, t);
-    case 4: return dataflow_T<4>(bj, B, ldb, X, ldx, t);
-    case 8: return dataflow_T<8>(bj, B, ldb, X, ldx, t);
-    case 16: return dataflow_T<16>(bj, B, ldb, X, ldx, t);
-    default: return dataflow_T<32>(bj, B, ldb, X, ldx, t);
-  }
-}
-
 }  // namespace
 
 extern "C" int pcu_bj_apply(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   PCU_CHECK(bj && B && X && t >= 1 && t <= 32, "pcu_bj_apply: bad arguments (t=%d, need 1..32)", t);
   PCU_CHECK(ldb >= t && ldx >= t, "pcu_bj_apply: leading dimension smaller than t");
   if (ensure_work(bj, pick_T(t))) return 1;
-  // PREALPS_BJ_LEVELS=1: one launch group per level of the forest (the round-1 path, kept for A/B runs and per-level profiles)
-  if (getenv("PREALPS_BJ_LEVELS") != nullptr || getenv("PREALPS_BJ_PROFILE") != nullptr) return dispatch_apply(bj, B, ldb, X, ldx, t);
-  return dispatch_dataflow(bj, B, ldb, X, ldx, t);
+  return dispatch_apply(bj, B, ldb, X, ldx, t);
 }

@@ -212,7 +212,8 @@ int preAlps_b200_BenchKernel(int what, int t, int reps, int flush_l2, float* ms_
   double *P = pool, *AP = pool + blk, *Z = pool + 2 * blk, *R = pool + 3 * blk, *X = pool + 4 * blk, *Pp = pool + 5 * blk,
          *APp = pool + 6 * blk, *sm = pool + 7 * blk;
   int* st = (int*)pcu_malloc(c, 16);
-  double tot = 0.0;
+  /* median of the timed repetitions */
+  float* samples = (float*)pa_xmalloc(sizeof(float) * (size_t)(reps > 0 ? reps : 1));
   for (int r = -2; r < reps; ++r) {  /* two untimed warm-up calls */
     if (flush_l2) pa_cuda_check(pcu_flush_l2(c), "pcu_flush_l2");
     pcu_timer_start(c, 2);
@@ -236,9 +237,16 @@ int preAlps_b200_BenchKernel(int what, int t, int reps, int flush_l2, float* ms_
     pcu_timer_stop(c, 2);
     float ms = 0.f;
     pa_cuda_check(pcu_timer_elapsed_ms(c, 2, &ms), "pcu_timer_elapsed_ms");
-    if (r >= 0) tot += ms;
+    if (r >= 0) samples[r] = ms;
   }
-  *ms_out = (float)(tot / (reps > 0 ? reps : 1));
+  for (int i = 1; i < reps; ++i) {  /* insertion sort */
+    const float v = samples[i];
+    int j = i - 1;
+    for (; j >= 0 && samples[j] > v; --j) samples[j + 1] = samples[j];
+    samples[j + 1] = v;
+  }
+  *ms_out = reps > 0 ? (reps % 2 ? samples[reps / 2] : 0.5f * (samples[reps / 2 - 1] + samples[reps / 2])) : 0.f;
+  free(samples);
   pcu_free(c, pool);
   pcu_free(c, st);
   return 0;

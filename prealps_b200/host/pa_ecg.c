@@ -69,7 +69,7 @@ static double* fu_beta1(ecg_priv_t* p) { return p->small + (size_t)p->t * p->t; 
 static double* fu_beta2(ecg_priv_t* p) { return p->small + 2 * (size_t)p->t * p->t; }
 static double* fu_mu(ecg_priv_t* p) { return p->small + 3 * (size_t)p->t * p->t; }
 static double* fu_rr(ecg_priv_t* p) { return p->small + 4 * (size_t)p->t * p->t; }
-static double* fu_U(ecg_priv_t* p) { return p->small + 5 * (size_t)p->t * p->t + 8; }
+/* behind sm_rr / rr_glob (6 t^2, 6 t^2 + 1): no view of the pool overlaps another one that is live at the same time */
 static double* fu_aout(ecg_priv_t* p) { return p->small + 6 * (size_t)p->t * p->t + 8; }
 
 static void set_shell(CPLM_Mat_Dense_t* s, double* val, int M, int m, int n, int ld) {
@@ -183,6 +183,28 @@ int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   p->fixed = 0;
   p->tprev = t;
   *rci_request = 0;
+  return 0;
+}
+
+/* ref: ecg.c:201-221 -- column colIndex of XSplit <- x, everything else untouched (the caller zeroed it).  XSplit is a
+ * library block in HBM or a caller's host block of either storage order. */
+int _preAlps_ECGSplit(double* x, CPLM_Mat_Dense_t* XSplit, int colIndex) {
+  if (!XSplit || !XSplit->val) CPLM_Abort(" wrong test 'XSplit->val != NULL'");
+  if (!x) CPLM_Abort(" wrong test 'x != NULL'");
+  const int m = XSplit->info.m;
+  if (pa_is_device_block(XSplit)) {
+    pcu_ctx* c = pa_ctx();
+    if (XSplit->info.stor_type != ROW_MAJOR) CPLM_Abort("device blocks must be ROW_MAJOR");
+    double* tmp = (double*)pcu_malloc(c, sizeof(double) * (size_t)(m > 0 ? m : 1));
+    if (!tmp) CPLM_Abort("device allocation failed: %s", pcu_last_error());
+    pa_cuda_check(pcu_h2d(c, tmp, x, sizeof(double) * (size_t)m), "pcu_h2d");
+    pa_cuda_check(pcu_copy_cols(c, m, 1, XSplit->val + colIndex, XSplit->info.lda, tmp, 1), "pcu_copy_cols");
+    pcu_free(c, tmp);
+    return 0;
+  }
+  const int row_major = XSplit->info.stor_type == ROW_MAJOR;
+  const size_t s1 = row_major ? (size_t)XSplit->info.n : 1, s2 = row_major ? 1 : (size_t)XSplit->info.m;
+  for (int i = 0; i < m; ++i) XSplit->val[i * s1 + colIndex * s2] = x[i];
   return 0;
 }
 
@@ -471,11 +493,16 @@ int pa_h_pivoted_chol(int n, double* A, int lda, int* piv, double tol) {
   return n;
 }
 
-/* Orthomin with ADAPT_BS (ref: ecg.c:360-393): after P <- Z the new directions are orthonormalised by a
- * rank-revealing Cholesky QR, P <- P[:, piv] U^-1 with P^T P [piv, piv] = U^T U.  With full rank -- the only case
- * the reference handles consistently: once the rank drops it keeps computing P^T P on the stale column count
- * (ecg.c:366 uses P's old info while the copy at ecg.c:357 moved nrhs columns) -- this is one more block pass;
- * a rank drop aborts with a message. */
+/* Orthomin with ADAPT_BS (ref: ecg.c:360-393): after P <- Z the T new directions are orthonormalised by a rank-revealing
+ * Cholesky QR: C = P^T P (all-reduced), C[piv, piv] = U^T U by dpstrf, which stops at the first pivot <= T eps max(diag):
+ * `rank` columns.  P <- P[:, piv[:rank]] U^-1 (dlapmt + dtrsm, ecg.c:380-385), block size <- rank (ecg.c:391).
+ * Here W = the T x T matrix with W[piv[k], j] = (U^-1)[k, j] (k <= j < rank) and zero columns from `rank` on, P <- P W in one
+ * pass: the dropped directions become zero columns, every block kernel keeps running at the full width T (exact), SpMM
+ * and block-Jacobi run on `rank` columns because the shells say so.
+ * The reference is only consistent up to its first rank drop: afterwards it keeps forming P^T P with the stale column
+ * count of P's info (ecg.c:366 after the copy of nrhs columns at :357) and factors an nrhs x nrhs array that is partly
+ * stale.  This code continues with the algorithm the reduction stands for: every iteration orthonormalises all T new
+ * directions Z - P beta again, the rank may shrink further (or recover), bs = rank. */
 static void omin_rrqr(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   pcu_ctx* c = pa_g.ctx;
   const int m = p->m, T = p->t, ld = p->ld;
@@ -490,31 +517,83 @@ static void omin_rrqr(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   t0 = pa_wtime();
   const int rank = pa_h_pivoted_chol(T, C, T, piv, -1.0);
   ecg->pstrf_t += pa_wtime() - t0;
-  if (rank < T)
-    CPLM_Abort("ADAPT_BS with ORTHOMIN: the new search directions lost rank (%d of %d); the reduction itself is not "
-               "implemented (the reference's own handling of this case is inconsistent, ecg.c:357-366)", rank, T);
+  for (int k = 0; k < T; ++k) ecg->iwork[k] = piv[k] + 1;  /* dpstrf's 1-based pivots, where the reference leaves them */
   t0 = pa_wtime();
-  pa_h_triu_inv(T, C, T, Ui, T);
   for (int i = 0; i < T * T; ++i) Wneg[i] = 0.0;
-  for (int j = 0; j < T; ++j) for (int k = 0; k <= j; ++k) Wneg[piv[k] + (size_t)T * j] = -Ui[k + (size_t)T * j];
+  if (rank > 0) {
+    pa_h_triu_inv(rank, C, T, Ui, T);
+    for (int j = 0; j < rank; ++j) for (int k = 0; k <= j; ++k) Wneg[piv[k] + (size_t)T * j] = -Ui[k + (size_t)T * j];
+  }
   pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
   /* P_prev's buffer is unused by Orthomin: P W is formed there and the two buffers trade places */
   pa_cuda_check(pcu_memset(c, p->Pp, 0, sizeof(double) * (size_t)m * ld), "pcu_memset");
   pa_cuda_check(pcu_update_z(c, m, T, p->Pp, ld, p->P, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
   double* old = p->P; p->P = p->Pp; p->Pp = old;
   ecg->lapmt_t += pa_wtime() - t0;
-  ecg->bs = T;
+  ecg->bs = rank;
+  if (rank < T) p->fixed = 1;  /* from here on the descent step takes the padded path below */
+}
+
+/* The "rci_request == 0" half of an Orthomin iteration once directions have been dropped (bs < T): P has zero columns
+ * from bs on, AP = A P was formed on bs columns only (the rest of its buffer is stale).  Everything at the full width T:
+ *   G = AP^T P, Gpr = P^T R (only G[:bs, :bs] and Gpr[:bs, :] are read); host: U = chol(G[:bs, :bs]) (ref: ecg.c:318-322),
+ *   W = diag(U^-1, 0), alpha = U^-T Gpr[:bs, :];  P <- P W, AP <- AP W (which also clears the stale columns);
+ *   X += P [alpha; 0], R -= AP [alpha; 0]   (ref: ecg.c:324-341). */
+static void omin_reduced_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
+  pcu_ctx* c = pa_g.ctx;
+  const int m = p->m, T = p->t, ld = p->ld, bs = ecg->bs;
+  double t0 = pa_wtime();
+  pa_cuda_check(pcu_gram2(c, m, T, p->AP, ld, p->P, ld, sm_G(p), p->P, ld, p->R, ld, sm_Gpr(p)), "pcu_gram2");
+  ecg->gemm_t += pa_wtime() - t0;
+  pa_allreduce_dev(sm_G(p), 2 * T * T, &ecg->comm_t);
+  double G[2 * 32 * 32], Ui[32 * 32], Wneg[32 * 32], Af[32 * 32];
+  pa_cuda_check(pcu_d2h(c, G, sm_G(p), sizeof(double) * 2 * (size_t)T * T), "pcu_d2h");
+  const double* Gpr = G + (size_t)T * T;
+  t0 = pa_wtime();
+  if (pa_h_chol_upper(bs, G, T) != 0) CPLM_Abort("ACHQR: dpotrf:\n ERROR: P^tAP is not spd!");  /* ref: ecg.c:320-322 */
+  ecg->potrf_t += pa_wtime() - t0;
+  t0 = pa_wtime();
+  pa_h_triu_inv(bs, G, T, Ui, bs);
+  for (int i = 0; i < T * T; ++i) { Wneg[i] = 0.0; Af[i] = 0.0; }
+  for (int j = 0; j < bs; ++j) for (int i = 0; i <= j; ++i) Wneg[i + (size_t)T * j] = -Ui[i + (size_t)bs * j];
+  for (int j = 0; j < T; ++j)
+    for (int i = 0; i < bs; ++i) {
+      double v = 0.0;
+      for (int k = 0; k <= i; ++k) v += Ui[k + (size_t)bs * i] * Gpr[k + (size_t)T * j];
+      Af[i + (size_t)T * j] = v;
+    }
+  pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  pa_cuda_check(pcu_h2d(c, sm_alpha(p), Af, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  const size_t blk = sizeof(double) * (size_t)m * ld;
+  /* Z (the old P buffer after the swap of the last iteration) and P_prev are both free here: scratch for P W and AP W */
+  pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");
+  pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->P, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
+  { double* o = p->P; p->P = p->Z; p->Z = o; }
+  pa_cuda_check(pcu_memset(c, p->Pp, 0, blk), "pcu_memset");
+  pa_cuda_check(pcu_update_z(c, m, T, p->Pp, ld, p->AP, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
+  { double* o = p->AP; p->AP = p->Pp; p->Pp = o; }
+  ecg->trsm_t += pa_wtime() - t0;
+  t0 = pa_wtime();
+  pa_cuda_check(pcu_update_xr(c, m, T, p->P, ld, p->AP, ld, sm_alpha(p), p->X, ld, p->R, ld, sm_rr(p)), "pcu_update_xr");
+  ecg->gemm_t += pa_wtime() - t0;
+  refresh_shells(ecg, p);
+  p->have_rr = 1;
+  ecg->iter++;
+  p->iter_since_reset++;
 }
 
 int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
   ecg_priv_t* p = priv_of(ecg);
   pcu_ctx* c = pa_g.ctx;
-  const int m = p->m, t = ecg->bs, ld = p->ld;
+  const int m = p->m, ld = p->ld;
   if (*rci_request == 0) {
-    descent_half_step(ecg, p);
+    if (p->fixed) omin_reduced_half_step(ecg, p);
+    else descent_half_step(ecg, p);
     *rci_request = 1;
   } else if (*rci_request == 1) {
-    /* beta = AP^T Z ; Z -= P beta ; P <- Z   (ref: ecg.c:345-359) */
+    /* beta = AP^T Z ; Z -= P beta ; P <- Z   (ref: ecg.c:345-359); after a reduction at the full width: the dropped
+     * columns of P and AP are zero, Z = M^-1 R always has T columns */
+    const int t = p->fixed ? p->t : ecg->bs;
     double t0 = pa_wtime();
     pa_cuda_check(pcu_gram2(c, m, t, p->AP, ld, p->Z, ld, sm_beta1(p), NULL, 0, NULL, 0, NULL), "pcu_gram2");
     ecg->gemm_t += pa_wtime() - t0;
@@ -679,7 +758,7 @@ int _preAlps_ECGIterateOdirFused(preAlps_ECG_t* ecg, int* rci_request) {
   else *rci_request = 0;
   if (p->adapt && !fused_adapt_step(ecg, p, Hs)) return 0;
   t0 = pa_wtime();
-  pa_cuda_check(pcu_fused_small(c, t, fu_mu(p), fu_beta1(p), fu_beta2(p), fu_U(p), p->status_dev), "pcu_fused_small");
+  pa_cuda_check(pcu_fused_small(c, t, fu_mu(p), fu_beta1(p), fu_beta2(p), NULL, p->status_dev), "pcu_fused_small");
   pa_cuda_check(pcu_right_solve(c, m, t, fu_mu(p), p->Z, ld), "pcu_right_solve");
   /* P,AP <- .U^-1 ; alpha = U^-T alpha ; X += P alpha ; R -= AP alpha */
   pa_cuda_check(pcu_ortho_update(c, m, t, fu_mu(p), fu_alpha(p), p->P, ld, p->AP, ld, p->X, ld, p->R, ld, NULL, fu_aout(p),
@@ -760,9 +839,15 @@ int preAlps_ECGFinalize(preAlps_ECG_t* ecg, double* solution) {
   return ierr;
 }
 
+static void print_info(const char* name, const CPLM_Mat_Dense_t* A) {  /* ref: cplm_matdense.c:315-325 */
+  if (!A) { printf("%s\n(released)\n", name); return; }
+  printf("%s\nDense Matrix %dx%d\tLocal Data: %dx%d\t%s\tLeading Dimension Array %d\tNumber of elements of array %d\n", name,
+         A->info.M, A->info.N, A->info.m, A->info.n, (A->info.stor_type == ROW_MAJOR) ? "Storage: Row major\n" : "Storage: Col major\n",
+         A->info.lda, A->info.nval);
+}
+
 void preAlps_ECGPrint(preAlps_ECG_t* ecg, int verbosity) {
   int rank = pa_g.rank;
-  (void)verbosity;
   printf("[%d] prints ECG_t...\n", rank);
   printf("=== Summary ===\n");
   printf("\titer: %d\n\tres : %e\n\tbs  : %1d\n", ecg->iter, ecg->res, ecg->bs);
@@ -778,5 +863,12 @@ void preAlps_ECGPrint(preAlps_ECG_t* ecg, int verbosity) {
   printf("\tgeqrf_t: %e s\n", ecg->geqrf_t);
   printf("\tormqr_t: %e s\n", ecg->ormqr_t);
   printf("\tcopy_t : %e s\n", ecg->copy_t);
+  if (verbosity > 1) {  /* ref: ecg.c:713-726; after Finalize the blocks are released (the reference reads freed memory there) */
+    printf("=== Memory consumption ===\n");
+    print_info("X", ecg->X); print_info("R", ecg->R); print_info("V", ecg->V); print_info("AV", ecg->AV);
+    print_info("P", ecg->P); print_info("AP", ecg->AP); print_info("Z", ecg->Z);
+    print_info("alpha", ecg->alpha); print_info("beta", ecg->beta);
+    printf("\n");
+  }
   printf("[%d] ends printing ECG_t!\n", rank);
 }

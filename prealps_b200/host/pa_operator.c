@@ -570,6 +570,7 @@ double preAlps_b200_Stat(const char* name) {
   if (!strcmp(name, "spmm_bytes_t8")) return g->spmm ? pcu_spmm_bytes(g->spmm, 8) : -1;
   if (!strncmp(name, "spmm_bytes_t", 12)) return g->spmm ? pcu_spmm_bytes(g->spmm, atoi(name + 12)) : -1;
   if (!strncmp(name, "bj_bytes_t", 10)) return g->bj ? pcu_bj_bytes(g->bj, atoi(name + 10)) : -1;
+  if (!strncmp(name, "bj_stored_bytes_t", 17)) return g->bj ? pcu_bj_stored_bytes(g->bj, atoi(name + 17)) : -1;
   if (!strcmp(name, "bj_nnz_exact")) return g->bj ? pcu_bj_stat(g->bj, 0) : -1;
   if (!strcmp(name, "bj_nnz_stored")) return g->bj ? pcu_bj_stat(g->bj, 1) : -1;
   if (!strcmp(name, "bj_supernodes")) return g->bj ? pcu_bj_stat(g->bj, 2) : -1;

@@ -1,5 +1,5 @@
 """Run under AddressSanitizer by tests/test_bj_emul.py::test_kernels_under_address_sanitizer (LD_PRELOAD=libasan):
-factorisation + sweeps of a small block, with the dataflow apply and with the level-by-level launches."""
+factorisation + sweeps of a small block, twice (same bits)."""
 import ctypes as C
 import os
 import sys
@@ -27,9 +27,6 @@ rp, ci, vv = (C.POINTER(C.c_int) * 1)(ip(rp_)), (C.POINTER(C.c_int) * 1)(ip(ci_)
 cuts = np.array([0, n], dtype=np.int32)
 out = []
 for lc in (0, 1):
-    os.environ.pop("PREALPS_BJ_LEVELS", None)
-    if lc:
-        os.environ["PREALPS_BJ_LEVELS"] = "1"
     bj = C.c_void_p()
     assert lib.pcu_bj_create(ctx, 1, ip(cuts), rp, ci, vv, C.byref(bj)) == 0
     for t in (1, 8):

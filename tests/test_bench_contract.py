@@ -27,7 +27,10 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "ecg_t8_bjacobi_iterations_per_s" and d["unit"] == "iterations/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["ms_per_step"] == pytest.approx(1000.0 / d["value"])
-    assert d["config"]["workload"].startswith("synthetic 3D Poisson 7-point 128^3 (2097152 rows), ECG t=8 + block Jacobi")
+    # --ref-n 12 is NOT the headline configuration, and the line says so: config names the grid that ran (with the default
+    # --ref-n the reference runs the same 128^3 as the GPU arm; that takes minutes and is left to the driver)
+    assert d["config"]["workload"].startswith("synthetic 3D Poisson 7-point 12^3 (1728 rows), ECG t=8 + block Jacobi")
+    assert d["config"]["n"] == 12 and d["cpu_baseline"]["sample_iterations"] == 7
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "12^3" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -1,7 +1,6 @@
 """The whole stack on the CPU emulation (tests/emul): the plain-C host layer (libprealps_b200) on top of every CUDA kernel of
 libprealps_cuda compiled against a miniature CUDA runtime -- operator build, block-Jacobi factorisation, ECG iterations --
-against a golden run of the reference and against the numpy restatement, and the opt-in kernel candidates against the
-default kernels bit for bit over a whole solve.  TEST INFRASTRUCTURE: logic and data flow only; the product libraries
+against a golden run of the reference and against the numpy restatement.  TEST INFRASTRUCTURE: logic and data flow only; the product libraries
 have no CPU path and the -m gpu tests remain the parity tests proper."""
 import json
 import os
@@ -16,8 +15,7 @@ import restate
 from conftest import GOLDEN, ROOT
 
 CASE = os.path.join(ROOT, "tests", "emul", "full_solve_case.py")
-CANDIDATE_VARS = ("PREALPS_SPMM_LEAN", "PREALPS_SPMM_BULK", "PREALPS_BJ_BOTTOM", "PREALPS_BJ_GRAPH", "PREALPS_BJ_ASM_PREFETCH",
-                  "PREALPS_SPMM_OVERLAP")
+CANDIDATE_VARS = ("PREALPS_SPMM_BULK", "PREALPS_SPMM_OVERLAP")
 
 
 def solve(spec, **switches):
@@ -30,9 +28,9 @@ def solve(spec, **switches):
     return r
 
 
-def test_candidates_over_a_whole_solve():
-    """t = 8 so that the SpMM candidates engage; every candidate keeps the operation order of the kernel it replaces, so
-    the residual history of the whole solve is the same bits"""
+def test_whole_solve_and_staging_variants():
+    """t = 8 so that the bulk-staging SpMM kernel engages; it keeps the operation order of the kernel it replaced, so the
+    residual history of the whole solve is the same bits with PREALPS_SPMM_BULK=0"""
     spec = "poisson7:8:8:8:1e-6"
     base = solve(spec)
     P = restate.Partitioned(gen_matrices.poisson7(8).tocsr(), 8)
@@ -40,11 +38,22 @@ def test_candidates_over_a_whole_solve():
     assert abs(base["iter"] - ref["iter"]) <= 1
     n = min(len(base["hist"]), len(ref["res_hist"]))
     assert np.allclose(base["hist"][:n], ref["res_hist"][:n], rtol=1e-6)
-    a = solve(spec, PREALPS_SPMM_LEAN="1", PREALPS_BJ_BOTTOM="2", PREALPS_BJ_GRAPH="1", PREALPS_BJ_ASM_PREFETCH="1")
-    b = solve(spec, PREALPS_SPMM_BULK="1", PREALPS_BJ_BOTTOM="99")
-    for r in (a, b):
-        assert r["iter"] == base["iter"] and np.array_equal(r["hist"], base["hist"]) and r["sol_sum"] == base["sol_sum"]
-        assert r["launches"] < base["launches"]
+    a = solve(spec, PREALPS_SPMM_BULK="0")
+    assert a["iter"] == base["iter"] and np.array_equal(a["hist"], base["hist"]) and a["sol_sum"] == base["sol_sum"]
+
+
+def test_orthomin_adapt_bs_rank_drop():
+    """Orthomin + ADAPT_BS when dpstrf drops a direction (ecg.c:375-391; round 1 aborted there): the golden from the
+    reference, where the drop is the last thing that happens, and a solve that continues on 3 of 4 directions, checked
+    inside the case script against the numpy restatement and a dense solve (tests/gpu_util.py: check_rank_drop_solve)"""
+    name = "poisson7_n4_s4_t4_omin_adapt_rankdrop"
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    r = solve(name)
+    assert r["iter"] == int(g["iter"]) and r["bs_hist"] == g["bs_hist"].tolist() and r["bs_hist"][-1] == 3
+    n = len(r["hist"])
+    assert np.allclose(r["hist"][:n - 1], g["res_hist"][:n - 1], rtol=1e-7)
+    r = solve("rankdrop")
+    assert r["bs_hist"][0] == 4 and r["bs_hist"][1] == 3 and r["iter"] > 8
 
 
 def test_unchanged_reference_driver_on_the_emulated_stack(tmp_path):

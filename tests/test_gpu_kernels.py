@@ -57,10 +57,6 @@ def test_spmm_matches_scipy(dev, t):
     cu.pcu_spmm_destroy(op)
 
 
-candidates = pytest.mark.skipif(not os.environ.get("PREALPS_TEST_CANDIDATES"),
-                                reason="opt-in kernels that have not been measured on a B200 yet (PREALPS_TEST_CANDIDATES=1)")
-
-
 @pytest.mark.parametrize("gen,N", [("poisson7", 14), ("stencil27", 9)])
 def test_spmm_bulk_staging_is_bit_identical(dev, gen, N, monkeypatch):
     """spmm_bulk_kernel (cp.async.bulk staging, the default from t = 8 up) keeps the mapping and the summation order of
@@ -233,49 +229,6 @@ def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t):
     assert cu.pcu_bj_apply(bj, dB, ld, dB, ld, t) == 0
     assert np.array_equal(dev.down(dB, (n, ld)), X)
     assert cu.pcu_bj_stat(bj, 0) > 0 and cu.pcu_bj_stat(bj, 1) >= cu.pcu_bj_stat(bj, 0)
-    dev.free(dB, dX)
-    cu.pcu_bj_destroy(bj)
-
-
-@pytest.mark.parametrize("t", [1, 3, 8, 16, 32])
-def test_block_jacobi_dataflow_apply_matches_the_level_by_level_launches(dev, t, monkeypatch):
-    """the default apply is ONE persistent launch whose work units wait on per-supernode counters (bj_solve.cu: apply_kernel);
-    PREALPS_BJ_LEVELS=1 is the launch group per level it replaces.  Same operation order per panel and per gather list:
-    same bits, on several subdomains and repeatedly (the counters are reset before every apply)."""
-    import scipy.sparse.linalg as spla
-    A = gen_matrices.poisson7(24).tocsr()
-    n = A.shape[0]
-    nb = 3
-    cuts = np.linspace(0, n, nb + 1).astype(np.int32)
-    blocks = [A[cuts[b]:cuts[b + 1], cuts[b]:cuts[b + 1]].tocsr() for b in range(nb)]
-    keep = []
-    for Bk in blocks:
-        U = sp.triu(Bk, format="csr")
-        U.sort_indices()
-        keep.append((U.indptr.astype(np.int32), U.indices.astype(np.int32), U.data.copy()))
-    rp = (C.POINTER(C.c_int) * nb)(*[capi.ip(k[0]) for k in keep])
-    ci = (C.POINTER(C.c_int) * nb)(*[capi.ip(k[1]) for k in keep])
-    vv = (C.POINTER(C.c_double) * nb)(*[capi.dp(k[2]) for k in keep])
-    bj = C.c_void_p()
-    assert cu.pcu_bj_create(dev.ctx, nb, capi.ip(cuts), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
-    ld = t if (t % 2 == 0 or t == 1) else t + 1
-    B = np.random.default_rng(t).standard_normal((n, ld))
-    dB, dX = dev.up(B), dev.zeros(n * ld)
-    out = []
-    for levels in ("1", None, None, "1", None):
-        if levels is None:
-            monkeypatch.delenv("PREALPS_BJ_LEVELS", raising=False)
-        else:
-            monkeypatch.setenv("PREALPS_BJ_LEVELS", levels)
-        assert cu.pcu_bj_apply(bj, dB, ld, dX, ld, t) == 0, cu.pcu_last_error()
-        out.append(dev.down(dX, (n, ld))[:, :t])
-    ref = np.vstack([spla.splu(Bk.tocsc()).solve(B[cuts[b]:cuts[b + 1], :t]) for b, Bk in enumerate(blocks)])
-    assert np.linalg.norm(out[0] - ref) <= 1e-11 * np.linalg.norm(ref)
-    for o in out[1:]:
-        assert np.array_equal(o, out[0])
-    monkeypatch.delenv("PREALPS_BJ_LEVELS", raising=False)
-    assert cu.pcu_bj_apply(bj, dB, ld, dB, ld, t) == 0   # in place
-    assert np.array_equal(dev.down(dB, (n, ld))[:, :t], out[0])
     dev.free(dB, dX)
     cu.pcu_bj_destroy(bj)
 

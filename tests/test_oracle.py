@@ -48,7 +48,7 @@ def test_rhs_and_ecg_history(name):
     adapt = "bs_red" in g.files and int(g["bs_red"]) == 1
     if adapt and int(g["ortho"]) == 1:
         out = restate.ecg_solve(P, t, float(g["tol"]), ortho=1, rrqr=True)
-        assert np.all(g["bs_hist"] == t)  # the rank never drops
+        assert np.array_equal(out["bs_hist"], g["bs_hist"])  # dpstrf drops a direction at the same iteration (rankdrop case)
     elif adapt and int(g["ortho"]) == 2:
         out = restate.ecg_solve_fused_adapt(P, t, float(g["tol"]))
         assert np.array_equal(out["bs_hist"], g["bs_hist"])
@@ -65,9 +65,10 @@ def test_rhs_and_ecg_history(name):
     # Orthodir amplifies rounding differences between two exact block solvers (SuperLU here, the shim
     # Cholesky in the golden run) up to ~1e-8 relative at the last iteration (measured: 1.0e-8 worst case)
     # (the elasticity operators with ADAPT_BS: 1.9e-6 at the last iteration, numpy SVD vs the reference's dgesvd + dormqr)
-    assert np.allclose(out["res_hist"], ref, rtol=1e-5 if adapt else 1e-7, atol=0)
+    # (atol: a residual of 1e-20, where the rank-drop golden ends, is rounding noise)
+    assert np.allclose(out["res_hist"], ref, rtol=1e-5 if adapt else 1e-7, atol=1e-16)
     assert np.allclose(out["res_hist"][:8], ref[:8], rtol=1e-10, atol=0)
     assert abs(out["normb"] - float(g["normb"])) <= 1e-14 * float(g["normb"])
     sol_ref = np.concatenate([g["r%d_sol" % r] for r in range(S)])
     assert np.linalg.norm(out["sol"] - sol_ref) <= (1e-7 if adapt else 1e-9) * np.linalg.norm(sol_ref)
-    assert out["true_relres"] < 10 * float(g["tol"])
+    assert out["true_relres"] < max(10 * float(g["tol"]), 1e-14)

@@ -19,13 +19,13 @@ for rx in relax:
     if rx != "default":
         os.environ["PREALPS_BJ_RELAX_BIG"], os.environ["PREALPS_BJ_RELAX_BIG_COLS"] = rx.split(":")
     assert capi.lib.preAlps_b200_BlockJacobiCreate() == 0
-    for mode in ("levels", "dataflow"):
+    for mode in ("levels",):
         os.environ.pop("PREALPS_BJ_LEVELS", None)
         if mode == "levels":
             os.environ["PREALPS_BJ_LEVELS"] = "1"
         ms = C.c_float()
         capi.lib.preAlps_b200_BenchKernel(1, t, 20, 1, C.byref(ms))
-        b, ex = capi.stat("bj_bytes_t%d" % t), 16.0 * capi.stat("bj_nnz_exact")
-        print("n=%d nsub=%d relax=%-10s %-9s t=%d: %.3f ms  stored %.2f GB -> %.1f GB/s   exact nnz(L) x 16 B = %.2f GB -> %.1f GB/s, levels %d"
+        b, ex = capi.stat("bj_stored_bytes_t%d" % t), capi.stat("bj_bytes_t%d" % t)
+        print("n=%d nsub=%d relax=%-10s %-9s t=%d: %.3f ms  stored %.2f GB -> %.1f GB/s   algorithmic (exact nnz(L)) %.2f GB -> %.1f GB/s, levels %d"
               % (n, nsub, rx, mode, t, ms.value, b / 1e9, b / ms.value / 1e6, ex / 1e9, ex / ms.value / 1e6, int(capi.stat("bj_levels"))), flush=True)
     os.environ.pop("PREALPS_BJ_LEVELS", None)
