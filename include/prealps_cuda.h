@@ -80,6 +80,8 @@ int pcu_exchange_ints(pcu_ctx* ctx, int nnbr, const int* nbr, const int* send_pt
                       const int* recv_ptr, int* recv_data);
 /* in-place sum of n doubles that live on the device (no-op for one rank) */
 int pcu_allreduce_sum(pcu_ctx* ctx, double* dbuf, int n);
+/* host array of n ints from rank `root` to every rank (staged through HBM, ncclBroadcast); no-op on one rank */
+int pcu_bcast_ints(pcu_ctx* ctx, int* host_data, long long n, int root);
 
 /* ------------------------------------------------------------- K1: CSR SpMM
  * Y (m x t) = A_loc * [X ; H].  A_loc has m rows; column c < m refers to row c
@@ -165,6 +167,11 @@ int pcu_ortho_update(pcu_ctx* ctx, int m, int t, const double* G, const double* 
  *   Replaces 2x dgemm at ref: ecg.c:500-501 (the un-fused form, used after a block-size reduction). */
 int pcu_update_xr(pcu_ctx* ctx, int m, int t, const double* P, int ldp, const double* AP, int ldap,
                   const double* alpha, double* X, int ldx, double* R, int ldr, double* rr);
+/* pcu_transform_update: ADAPT_BS after a reduction (ref: ecg.c:470-501): P <- P Wm and AP <- AP Wm in place, X += P_old Wx,
+ *   R -= AP_old Wx, rr[0] = ||R||_F^2 local part, Wm / Wx general t x t column-major.  AP, X, R (and Wx) may be NULL.
+ *   Replaces dormqr/dtrsm + 2x dgemm of the reference in one pass over the blocks. */
+int pcu_transform_update(pcu_ctx* ctx, int m, int t, const double* Wm, const double* Wx, double* P, int ldp, double* AP,
+                         int ldap, double* X, int ldx, double* R, int ldr, double* rr);
 /* pcu_update_z: Z -= P beta1 + Pprev beta2 with beta1 (t1 x tz) and beta2 (t2 x tz) column-major,
  *   tight leading dimensions; Pprev/beta2 may be NULL with t2 = 0.
  *   Replaces dgemm at ref: ecg.c:517 (V = [P, P_prev], beta = [beta1; beta2]) and ecg.c:354. */

@@ -33,6 +33,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, nccl_uid_t, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -54,6 +55,7 @@ static int load_nccl() {
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
+  SYM(Broadcast, "ncclBroadcast")
   SYM(Send, "ncclSend")
   SYM(Recv, "ncclRecv")
   SYM(GroupStart, "ncclGroupStart")
@@ -273,6 +275,19 @@ int pcu_exchange_ints(pcu_ctx* c, int nnbr, const int* nbr, const int* send_ptr,
   if (nr) PCU_CUDA(cudaMemcpyAsync(recv_data, dr, sizeof(int) * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
   PCU_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(ds); cudaFree(dr);
+  return 0;
+}
+
+int pcu_bcast_ints(pcu_ctx* c, int* host_data, long long n, int root) {
+  if (c->nranks == 1 || n == 0) return 0;
+  PCU_CHECK(c->nccl_comm != nullptr, "pcu_bcast_ints: NCCL communicator not initialised");
+  int* d = nullptr;
+  PCU_CUDA(cudaMalloc(&d, sizeof(int) * (size_t)n));
+  if (c->rank == root) PCU_CUDA(cudaMemcpyAsync(d, host_data, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  PCU_NCCL(g_nccl.Broadcast(d, d, (size_t)n, kNcclInt32, root, c->nccl_comm, c->stream));
+  if (c->rank != root) PCU_CUDA(cudaMemcpyAsync(host_data, d, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  PCU_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
   return 0;
 }
 

@@ -735,6 +735,74 @@ __global__ void __launch_bounds__(kThreads) update_xr_kernel(int m, int t, const
   }
 }
 
+// ADAPT_BS after a reduction: P <- P Wm, AP <- AP Wm (in place, row by row), X += P_old Wx, R -= AP_old Wx, rr = ||R||^2,
+// with Wm and Wx general t x t matrices built on the host (column-major, tight ld).  AP / X / R may be null.
+// One pass over the four blocks instead of memset + product into a scratch block + copy back for each of P and AP and a
+// separate X / R update (19 block passes -> 8).
+template <int T>
+__global__ void __launch_bounds__(kThreads) transform_update_kernel(int m, int t, const double* __restrict__ Wm,
+                                                                    const double* __restrict__ Wx, double* P, int ldp,
+                                                                    double* AP, int ldap, double* X, int ldx, double* R,
+                                                                    int ldr, double* __restrict__ rr_partials) {
+  __shared__ double sWm[T * T];
+  __shared__ double sWx[T * T];
+  __shared__ double sred[kThreads / 32];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < t * t; e += kThreads) { sWm[e] = Wm[e]; sWx[e] = Wx ? Wx[e] : 0.0; }
+  __syncthreads();
+  double rr = 0.0;
+  for (int64_t r = (int64_t)blockIdx.x * kThreads + tid; r < m; r += (int64_t)gridDim.x * kThreads) {
+    double p[T];
+#pragma unroll
+    for (int a = 0; a < T; ++a) p[a] = (a < t) ? P[r * ldp + a] : 0.0;
+    if (X) {
+#pragma unroll
+      for (int c = 0; c < T; ++c) if (c < t) {
+        double s = X[r * ldx + c];
+#pragma unroll
+        for (int a = 0; a < T; ++a) if (a < t) s = fma(p[a], sWx[a + c * t], s);
+        X[r * ldx + c] = s;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < T; ++c) if (c < t) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < T; ++a) if (a < t) s = fma(p[a], sWm[a + c * t], s);
+      P[r * ldp + c] = s;
+    }
+    if (AP) {
+#pragma unroll
+      for (int a = 0; a < T; ++a) p[a] = (a < t) ? AP[r * ldap + a] : 0.0;
+      if (R) {
+#pragma unroll
+        for (int c = 0; c < T; ++c) if (c < t) {
+          double s = R[r * ldr + c];
+#pragma unroll
+          for (int a = 0; a < T; ++a) if (a < t) s = fma(-p[a], sWx[a + c * t], s);
+          R[r * ldr + c] = s;
+          rr = fma(s, s, rr);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < T; ++c) if (c < t) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < T; ++a) if (a < t) s = fma(p[a], sWm[a + c * t], s);
+        AP[r * ldap + c] = s;
+      }
+    }
+  }
+  rr = warp_sum(rr);
+  if ((tid & 31) == 0) sred[tid >> 5] = rr;
+  __syncthreads();
+  if (tid == 0 && rr_partials) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) s += sred[w];
+    rr_partials[blockIdx.x] = s;
+  }
+}
+
 // Z -= P b1 + Pprev b2 ; b1 is t1 x tz, b2 is t2 x tz, both column-major with tight ld
 template <int T>
 __global__ void __launch_bounds__(kThreads) update_z_kernel(int m, int tz, double* Z, int ldz,
@@ -979,6 +1047,22 @@ int pcu_update_xr(pcu_ctx* c, int m, int t, const double* P, int ldp, const doub
                                                                               ldr, c->red_partials));
   PCU_LAUNCH_CHECK(c);
   if (rr) {
+    reduce_partials_kernel<<<1, 32, 0, c->stream>>>(c->red_partials, grid, 1, rr, 1, nullptr);
+    PCU_LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+
+int pcu_transform_update(pcu_ctx* c, int m, int t, const double* Wm, const double* Wx, double* P, int ldp, double* AP, int ldap,
+                         double* X, int ldx, double* R, int ldr, double* rr) {
+  PCU_CHECK(c && Wm && P && t >= 1 && t <= kMaxT, "pcu_transform_update: bad arguments (t=%d)", t);
+  PCU_CHECK((X == nullptr) == (R == nullptr) && (!X || (Wx && AP)), "pcu_transform_update: X, R, Wx and AP go together");
+  const int grid = stream_grid(c, m, kThreads, kWaves);
+  if (ensure_partials(c, (size_t)grid + 16)) return 1;
+  DISPATCH_T(pick_T(t), transform_update_kernel<TT><<<grid, kThreads, 0, c->stream>>>(m, t, Wm, Wx, P, ldp, AP, ldap, X, ldx, R, ldr,
+                                                                                     c->red_partials));
+  PCU_LAUNCH_CHECK(c);
+  if (R && rr) {
     reduce_partials_kernel<<<1, 32, 0, c->stream>>>(c->red_partials, grid, 1, rr, 1, nullptr);
     PCU_LAUNCH_CHECK(c);
   }

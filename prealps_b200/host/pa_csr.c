@@ -297,6 +297,35 @@ int pa_permute_sym(const CPLM_Mat_CSR_t* A, const int* perm, CPLM_Mat_CSR_t* B) 
   return 0;
 }
 
+/* rows [r0, r1) of P A P^T without forming the rest of it: what pa_permute_sym + pa_row_panel give, entry for entry (a
+ * process that owns a few subdomains of a 16.8 M-row operator permutes 1/8 of it) */
+int pa_permute_panel(const CPLM_Mat_CSR_t* A, const int* perm, int r0, int r1, CPLM_Mat_CSR_t* B) {
+  const int m = A->info.m, lm = r1 - r0;
+  int* iperm = (int*)pa_xmalloc(sizeof(int) * (size_t)m);
+  for (int i = 0; i < m; ++i) iperm[perm[i]] = i;
+  long long lnnz = 0;
+  for (int i = r0; i < r1; ++i) lnnz += A->rowPtr[perm[i] + 1] - A->rowPtr[perm[i]];
+  B->info = A->info;
+  B->info.M = A->info.m;
+  B->info.nnz = A->info.lnnz;
+  B->info.m = lm;
+  B->info.lnnz = (int)lnnz;
+  B->rowPtr = (int*)pa_xmalloc(sizeof(int) * ((size_t)lm + 1));
+  B->colInd = (int*)pa_xmalloc(sizeof(int) * (size_t)(lnnz > 0 ? lnnz : 1));
+  B->val = (double*)pa_xmalloc(sizeof(double) * (size_t)(lnnz > 0 ? lnnz : 1));
+  B->rowPtr[0] = 0;
+  for (int i = 0; i < lm; ++i) {
+    const int o = perm[r0 + i], n = A->rowPtr[o + 1] - A->rowPtr[o];
+    int* bc = B->colInd + B->rowPtr[i];
+    double* bv = B->val + B->rowPtr[i];
+    for (int k = 0; k < n; ++k) { bc[k] = iperm[A->colInd[A->rowPtr[o] + k]]; bv[k] = A->val[A->rowPtr[o] + k]; }
+    sort_row(bc, bv, n);
+    B->rowPtr[i + 1] = B->rowPtr[i] + n;
+  }
+  free(iperm);
+  return 0;
+}
+
 /* ref: CPLM_MatCSRGetRowPanel, cplm_v0_matcsr.c:655-720: rows [r0, r1) with global columns,
  * rowPtr rebased; info.M <- parent's m, info.nnz <- parent's lnnz. */
 int pa_row_panel(const CPLM_Mat_CSR_t* A, int r0, int r1, CPLM_Mat_CSR_t* B) {

@@ -33,7 +33,7 @@
 typedef struct {
   preAlps_ECG_t* owner;
   int m, t, ld;
-  double* buf[8];       /* P, Pprev, AP, APprev, Z, R, X (roles rotate) + a scratch block (ADAPT_BS with ORTHODIR_FUSED) */
+  double* buf[7];       /* P, Pprev, AP, APprev, Z, R, X (roles rotate) */
   int nbuf;
   double *P, *Pp, *AP, *APp, *Z, *R, *X;
   double* small;        /* G | Gpr | U | alpha | beta1 | beta2 | rr_local | rr_glob */
@@ -45,7 +45,7 @@ typedef struct {
   /* ADAPT_BS: after the first reduction the buffers stop rotating (slot0 = P/AP, slot1 = Pp/APp) */
   int adapt, fixed;
   int tprev;            /* columns of slot1 that still take part in the A-orthogonalisation (kbs - t) */
-  double* scratch;      /* 8th block */
+  int zcols_clean;      /* ADAPT_BS: the columns of Z beyond bs are known to be zero */
 } ecg_priv_t;
 
 #define MAX_SOLVERS 16
@@ -104,7 +104,7 @@ int _preAlps_ECGMalloc(preAlps_ECG_t* ecg) {
   const size_t blk = (size_t)m * p->ld;
   const size_t smalls = 8 * (size_t)t * t + 16;
   /* one pool, like the reference's mkl_calloc(7mt + 3t^2) (ref: ecg.c:58-62), but in HBM */
-  p->nbuf = (ecg->bs_red == ADAPT_BS && ecg->ortho_alg == ORTHODIR_FUSED) ? 8 : 7;
+  p->nbuf = 7;
   ecg->work = (double*)pcu_malloc(c, sizeof(double) * (p->nbuf * blk + smalls + 8));
   if (!ecg->work) CPLM_Abort("device allocation of the ECG pool failed: %s", pcu_last_error());
   pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * (p->nbuf * blk + smalls + 8)), "pcu_memset");
@@ -138,17 +138,18 @@ int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   const size_t blk = (size_t)m * p->ld;
   p->P = p->buf[0]; p->Pp = p->buf[1]; p->AP = p->buf[2]; p->APp = p->buf[3];
   p->Z = p->buf[4]; p->R = p->buf[5]; p->X = p->buf[6];
-  p->scratch = p->nbuf > 7 ? p->buf[7] : NULL;
   pa_cuda_check(pcu_memset(c, ecg->work, 0, sizeof(double) * p->nbuf * blk), "pcu_memset");
   /* ||b||: per-subdomain sums in row order, then summed over subdomains/processes (ref: ecg.c:143-155) */
   double nb = 0.0;
   int* cor = (int*)pa_xmalloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
   const int nsub = g->built ? g->s_hi - g->s_lo : 1;
+  double* nb_parts = (double*)pa_xcalloc((size_t)nsub, sizeof(double));
   for (int s = 0; s < nsub; ++s) {
     const int r0 = g->built ? g->rowPos[g->s_lo + s] - g->g0 : 0;
     const int r1 = g->built ? g->rowPos[g->s_lo + s + 1] - g->g0 : m;
     double part = 0.0;
     for (int i = r0; i < r1; ++i) part += rhs[i] * rhs[i];  /* == pow(x, 2) bit for bit */
+    nb_parts[s] = part;
     nb += part;
     /* R0 = T(b): the rows of subdomain s feed column s % t (ref: ecg.c:162 with rank -> subdomain id) */
     const int col = ((g->built ? g->s_lo : g->rank) + s) % t;
@@ -158,11 +159,12 @@ int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
     const double t0 = pa_wtime();
     MPI_Allreduce(MPI_IN_PLACE, &nb, 1, MPI_DOUBLE, MPI_SUM, ecg->comm);
     ecg->comm_t += pa_wtime() - t0;
-  } else if (g->nproc > 1 && g->xport == PA_XPORT_NCCL) {
-    pa_cuda_check(pcu_h2d(c, sm_rr(p), &nb, sizeof(double)), "pcu_h2d");
-    pa_allreduce_dev(sm_rr(p), 1, &ecg->comm_t);
-    pa_cuda_check(pcu_d2h(c, &nb, sm_rr(p), sizeof(double)), "pcu_d2h");
+  } else if (g->nproc > 1 && g->xport == PA_XPORT_NCCL && g->built) {
+    const double t0 = pa_wtime();
+    nb = pa_sum_over_subdomains(nb_parts);  /* rank order of the reference's reduction, whatever the number of GPUs */
+    ecg->comm_t += pa_wtime() - t0;
   }
+  free(nb_parts);
   ecg->normb = sqrt(nb);
   ecg->res = 1.0;
   ecg->iter = 0;
@@ -181,6 +183,7 @@ int _preAlps_ECGReset(preAlps_ECG_t* ecg, double* rhs, int* rci_request) {
   p->iter_since_reset = 0;
   p->adapt = (ecg->bs_red == ADAPT_BS);
   p->fixed = 0;
+  p->zcols_clean = 0;
   p->tprev = t;
   *rci_request = 0;
   return 0;
@@ -343,6 +346,15 @@ void pa_h_left_svd(int t, int n, const double* A, int lda, double* sv, double* Q
  *     slot0 <- slot0 * diag(W, I);  X += slot0 * [Q^T alpha (first t1 rows); 0];  R -= A slot0 * [..]
  *     bs = t1, kbs = T + (bs before) (ecg.c:491-492): the columns of slot1 beyond the old bs leave the
  *     A-orthogonalisation for good and are zeroed. */
+static void small_matmul(int T, const double* A, const double* B, double* C) {  /* C = A B, T x T column-major */
+  for (int j = 0; j < T; ++j)
+    for (int i = 0; i < T; ++i) {
+      double v = 0.0;
+      for (int k = 0; k < T; ++k) v += A[i + (size_t)T * k] * B[k + (size_t)T * j];
+      C[i + (size_t)T * j] = v;
+    }
+}
+
 static void adapt_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   pcu_ctx* c = pa_g.ctx;
   const int m = p->m, T = p->t, ld = p->ld, bs = ecg->bs;
@@ -378,36 +390,34 @@ static void adapt_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
                                    sm_alpha(p), sm_rr(p), p->status_dev), "pcu_ortho_update");
     ecg->trsm_t += pa_wtime() - t0;
   } else {
-    /* Wneg = -diag(W, I) and Af = [alpha'; 0], T x T column-major */
-    double Wneg[32 * 32], Af[32 * 32];
-    for (int i = 0; i < T * T; ++i) { Wneg[i] = 0.0; Af[i] = 0.0; }
-    for (int j = 0; j < T; ++j) Wneg[j + (size_t)T * j] = -1.0;
+    /* W = diag(W, I), Af = [alpha'; 0] and Wx = W Af, T x T column-major: slot0 <- slot0 W, X += slot0_old Wx, ... */
+    double W[32 * 32], Af[32 * 32], Wx[32 * 32];
+    for (int i = 0; i < T * T; ++i) { W[i] = 0.0; Af[i] = 0.0; }
+    for (int j = 0; j < T; ++j) W[j + (size_t)T * j] = 1.0;
     const int keep = reduce ? t1 : bs;
     for (int j = 0; j < bs; ++j)
       for (int i = 0; i < bs; ++i) {
         double v = 0.0;
         if (reduce) { for (int k = i; k < bs; ++k) v += Ui[i + (size_t)bs * k] * Q[k + (size_t)bs * j]; }
         else v = Ui[i + (size_t)bs * j];
-        Wneg[i + (size_t)T * j] = -v;
+        W[i + (size_t)T * j] = v;
       }
     for (int j = 0; j < T; ++j)
       for (int i = 0; i < keep; ++i) Af[i + (size_t)T * j] = reduce ? rows[(size_t)i * T + j] : alpha[i + (size_t)bs * j];
-    pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
-    pa_cuda_check(pcu_h2d(c, sm_alpha(p), Af, sizeof(double) * (size_t)T * T), "pcu_h2d");
+    small_matmul(T, W, Af, Wx);
+    pa_cuda_check(pcu_h2d(c, sm_U(p), W, sizeof(double) * (size_t)T * T), "pcu_h2d");
+    pa_cuda_check(pcu_h2d(c, sm_alpha(p), Wx, sizeof(double) * (size_t)T * T), "pcu_h2d");
     t0 = pa_wtime();
-    const size_t blk = sizeof(double) * (size_t)m * ld;
-    /* Z is free between the end of one iteration and the next preconditioner call: scratch for slot0 * W */
-    pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");
-    pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->P, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
-    pa_cuda_check(pcu_d2d(c, p->P, p->Z, blk), "pcu_d2d");
-    pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");
-    pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->AP, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
-    pa_cuda_check(pcu_d2d(c, p->AP, p->Z, blk), "pcu_d2d");
-    pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");  /* columns >= bs of Z stay zero from here on */
+    /* one pass: slot0 <- slot0 W, A slot0 likewise, X += .., R -= .., ||R||^2 (pcu_transform_update) */
+    pa_cuda_check(pcu_transform_update(c, m, T, sm_U(p), sm_alpha(p), p->P, ld, p->AP, ld, p->X, ld, p->R, ld, sm_rr(p)),
+                  "pcu_transform_update");
     ecg->ormqr_t += pa_wtime() - t0;
-    t0 = pa_wtime();
-    pa_cuda_check(pcu_update_xr(c, m, T, p->P, ld, p->AP, ld, sm_alpha(p), p->X, ld, p->R, ld, sm_rr(p)), "pcu_update_xr");
-    ecg->gemm_t += pa_wtime() - t0;
+    /* the columns of Z beyond the live directions must read as zero in the full-width passes of the other half step:
+     * block-Jacobi only writes bs columns from now on */
+    if (reduce || !p->zcols_clean) {
+      pa_cuda_check(pcu_zero_cols(c, m, T - keep, p->Z + keep, ld), "pcu_zero_cols");
+      p->zcols_clean = 1;
+    }
     if (reduce) {
       ecg->bs = t1;
       ecg->kbs = bs + T;
@@ -510,7 +520,7 @@ static void omin_rrqr(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   pa_cuda_check(pcu_gram2(c, m, T, p->P, ld, p->P, ld, sm_G(p), NULL, 0, NULL, 0, NULL), "pcu_gram2");
   ecg->gemm_t += pa_wtime() - t0;
   pa_allreduce_dev(sm_G(p), T * T, &ecg->comm_t);
-  double C[32 * 32], Ui[32 * 32], Wneg[32 * 32];
+  double C[32 * 32], Ui[32 * 32], W[32 * 32];
   int piv[32];
   pa_cuda_check(pcu_d2h(c, C, sm_G(p), sizeof(double) * (size_t)T * T), "pcu_d2h");
   for (int j = 0; j < T; ++j) for (int i = j + 1; i < T; ++i) C[i + (size_t)T * j] = C[j + (size_t)T * i];  /* 'U' triangle */
@@ -519,16 +529,13 @@ static void omin_rrqr(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   ecg->pstrf_t += pa_wtime() - t0;
   for (int k = 0; k < T; ++k) ecg->iwork[k] = piv[k] + 1;  /* dpstrf's 1-based pivots, where the reference leaves them */
   t0 = pa_wtime();
-  for (int i = 0; i < T * T; ++i) Wneg[i] = 0.0;
+  for (int i = 0; i < T * T; ++i) W[i] = 0.0;
   if (rank > 0) {
     pa_h_triu_inv(rank, C, T, Ui, T);
-    for (int j = 0; j < rank; ++j) for (int k = 0; k <= j; ++k) Wneg[piv[k] + (size_t)T * j] = -Ui[k + (size_t)T * j];
+    for (int j = 0; j < rank; ++j) for (int k = 0; k <= j; ++k) W[piv[k] + (size_t)T * j] = Ui[k + (size_t)T * j];
   }
-  pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
-  /* P_prev's buffer is unused by Orthomin: P W is formed there and the two buffers trade places */
-  pa_cuda_check(pcu_memset(c, p->Pp, 0, sizeof(double) * (size_t)m * ld), "pcu_memset");
-  pa_cuda_check(pcu_update_z(c, m, T, p->Pp, ld, p->P, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
-  double* old = p->P; p->P = p->Pp; p->Pp = old;
+  pa_cuda_check(pcu_h2d(c, sm_U(p), W, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  pa_cuda_check(pcu_transform_update(c, m, T, sm_U(p), NULL, p->P, ld, NULL, 0, NULL, 0, NULL, 0, NULL), "pcu_transform_update");
   ecg->lapmt_t += pa_wtime() - t0;
   ecg->bs = rank;
   if (rank < T) p->fixed = 1;  /* from here on the descent step takes the padded path below */
@@ -546,7 +553,7 @@ static void omin_reduced_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   pa_cuda_check(pcu_gram2(c, m, T, p->AP, ld, p->P, ld, sm_G(p), p->P, ld, p->R, ld, sm_Gpr(p)), "pcu_gram2");
   ecg->gemm_t += pa_wtime() - t0;
   pa_allreduce_dev(sm_G(p), 2 * T * T, &ecg->comm_t);
-  double G[2 * 32 * 32], Ui[32 * 32], Wneg[32 * 32], Af[32 * 32];
+  double G[2 * 32 * 32], Ui[32 * 32], W[32 * 32], Af[32 * 32], Wx[32 * 32];
   pa_cuda_check(pcu_d2h(c, G, sm_G(p), sizeof(double) * 2 * (size_t)T * T), "pcu_d2h");
   const double* Gpr = G + (size_t)T * T;
   t0 = pa_wtime();
@@ -554,28 +561,21 @@ static void omin_reduced_half_step(preAlps_ECG_t* ecg, ecg_priv_t* p) {
   ecg->potrf_t += pa_wtime() - t0;
   t0 = pa_wtime();
   pa_h_triu_inv(bs, G, T, Ui, bs);
-  for (int i = 0; i < T * T; ++i) { Wneg[i] = 0.0; Af[i] = 0.0; }
-  for (int j = 0; j < bs; ++j) for (int i = 0; i <= j; ++i) Wneg[i + (size_t)T * j] = -Ui[i + (size_t)bs * j];
+  for (int i = 0; i < T * T; ++i) { W[i] = 0.0; Af[i] = 0.0; }
+  for (int j = 0; j < bs; ++j) for (int i = 0; i <= j; ++i) W[i + (size_t)T * j] = Ui[i + (size_t)bs * j];
   for (int j = 0; j < T; ++j)
     for (int i = 0; i < bs; ++i) {
       double v = 0.0;
       for (int k = 0; k <= i; ++k) v += Ui[k + (size_t)bs * i] * Gpr[k + (size_t)T * j];
       Af[i + (size_t)T * j] = v;
     }
-  pa_cuda_check(pcu_h2d(c, sm_U(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
-  pa_cuda_check(pcu_h2d(c, sm_alpha(p), Af, sizeof(double) * (size_t)T * T), "pcu_h2d");
-  const size_t blk = sizeof(double) * (size_t)m * ld;
-  /* Z (the old P buffer after the swap of the last iteration) and P_prev are both free here: scratch for P W and AP W */
-  pa_cuda_check(pcu_memset(c, p->Z, 0, blk), "pcu_memset");
-  pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->P, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
-  { double* o = p->P; p->P = p->Z; p->Z = o; }
-  pa_cuda_check(pcu_memset(c, p->Pp, 0, blk), "pcu_memset");
-  pa_cuda_check(pcu_update_z(c, m, T, p->Pp, ld, p->AP, ld, T, sm_U(p), NULL, 0, 0, NULL), "pcu_update_z");
-  { double* o = p->AP; p->AP = p->Pp; p->Pp = o; }
+  small_matmul(T, W, Af, Wx);
+  pa_cuda_check(pcu_h2d(c, sm_U(p), W, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  pa_cuda_check(pcu_h2d(c, sm_alpha(p), Wx, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  /* P <- P W, AP <- AP W (which also clears the stale columns of AP), X += P_old W Af, R -= AP_old W Af: one pass */
+  pa_cuda_check(pcu_transform_update(c, m, T, sm_U(p), sm_alpha(p), p->P, ld, p->AP, ld, p->X, ld, p->R, ld, sm_rr(p)),
+                "pcu_transform_update");
   ecg->trsm_t += pa_wtime() - t0;
-  t0 = pa_wtime();
-  pa_cuda_check(pcu_update_xr(c, m, T, p->P, ld, p->AP, ld, sm_alpha(p), p->X, ld, p->R, ld, sm_rr(p)), "pcu_update_xr");
-  ecg->gemm_t += pa_wtime() - t0;
   refresh_shells(ecg, p);
   p->have_rr = 1;
   ecg->iter++;
@@ -608,14 +608,6 @@ int _preAlps_ECGIterateOmin(preAlps_ECG_t* ecg, int* rci_request) {
     *rci_request = 0;
   }
   return 0;
-}
-
-/* scratch <- block * (-Wneg) with Wneg T x T on the device; the block and the scratch buffer then trade places */
-static void right_multiply(ecg_priv_t* p, double** block, const double* Wneg_dev) {
-  pcu_ctx* c = pa_g.ctx;
-  pa_cuda_check(pcu_memset(c, p->scratch, 0, sizeof(double) * (size_t)p->m * p->ld), "pcu_memset");
-  pa_cuda_check(pcu_update_z(c, p->m, p->t, p->scratch, p->ld, *block, p->ld, p->t, Wneg_dev, NULL, 0, 0, NULL), "pcu_update_z");
-  double* old = *block; *block = p->scratch; p->scratch = old;
 }
 
 /* ORTHODIR_FUSED with ADAPT_BS (ref: ecg.c:532-658, reduction at :593-641). Same slot layout and zero/identity
@@ -671,15 +663,15 @@ static int fused_adapt_step(preAlps_ECG_t* ecg, ecg_priv_t* p, const double* H) 
     }
     for (int i = 0; i < bs; ++i) B1[i + (size_t)T * j] = tmp[i];
   }
-  /* Wneg = -diag(U^-1 Q, I); Bf1 = [Q^T B1p Q; B1h Q]; Bf2 = B2 Q; Af = [Q^T alpha (keep rows); 0] -- T x T */
-  double Wneg[32 * 32], Bf1[32 * 32], Bf2[32 * 32], Af[32 * 32];
-  for (int i = 0; i < T * T; ++i) { Wneg[i] = 0.0; Bf1[i] = 0.0; Bf2[i] = 0.0; Af[i] = 0.0; }
-  for (int j = 0; j < T; ++j) Wneg[j + (size_t)T * j] = -1.0;
+  /* W = diag(U^-1 Q, I); Bf1 = [Q^T B1p Q; B1h Q]; Bf2 = B2 Q; Af = [Q^T alpha (keep rows); 0]; Wx = W Af -- T x T */
+  double W[32 * 32], Bf1[32 * 32], Bf2[32 * 32], Af[32 * 32], Wx[32 * 32];
+  for (int i = 0; i < T * T; ++i) { W[i] = 0.0; Bf1[i] = 0.0; Bf2[i] = 0.0; Af[i] = 0.0; }
+  for (int j = 0; j < T; ++j) W[j + (size_t)T * j] = 1.0;
   for (int j = 0; j < bs; ++j)
     for (int i = 0; i < bs; ++i) {
       double v = 0.0;
       for (int k = i; k < bs; ++k) v += Ui[i + (size_t)bs * k] * Q[k + (size_t)bs * j];
-      Wneg[i + (size_t)T * j] = -v;
+      W[i + (size_t)T * j] = v;
     }
   for (int j = 0; j < bs; ++j)       /* tmp2 = B1 Q and B2 Q (T x bs) */
     for (int i = 0; i < T; ++i) {
@@ -698,19 +690,20 @@ static int fused_adapt_step(preAlps_ECG_t* ecg, ecg_priv_t* p, const double* H) 
   const int keep = reduce ? t1 : bs;
   for (int j = 0; j < T; ++j)
     for (int i = 0; i < keep; ++i) Af[i + (size_t)T * j] = reduce ? rows[(size_t)i * T + j] : alpha[i + (size_t)bs * j];
-  pa_cuda_check(pcu_h2d(c, fu_mu(p), Wneg, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  small_matmul(T, W, Af, Wx);
+  pa_cuda_check(pcu_h2d(c, fu_mu(p), W, sizeof(double) * (size_t)T * T), "pcu_h2d");
   pa_cuda_check(pcu_h2d(c, fu_beta1(p), Bf1, sizeof(double) * (size_t)T * T), "pcu_h2d");
   pa_cuda_check(pcu_h2d(c, fu_beta2(p), Bf2, sizeof(double) * (size_t)T * T), "pcu_h2d");
-  pa_cuda_check(pcu_h2d(c, fu_alpha(p), Af, sizeof(double) * (size_t)T * T), "pcu_h2d");
+  pa_cuda_check(pcu_h2d(c, fu_alpha(p), Wx, sizeof(double) * (size_t)T * T), "pcu_h2d");
   t0 = pa_wtime();
-  right_multiply(p, &p->P, fu_mu(p));
-  right_multiply(p, &p->AP, fu_mu(p));
-  right_multiply(p, &p->Z, fu_mu(p));
+  /* slot0 <- slot0 W, A slot0 likewise, X += slot0_old W Af, R -= A slot0_old W Af, ||R||^2: one pass; then Z <- Z W in place */
+  pa_cuda_check(pcu_transform_update(c, m, T, fu_mu(p), fu_alpha(p), p->P, ld, p->AP, ld, p->X, ld, p->R, ld, sm_rr(p)),
+                "pcu_transform_update");
+  pa_cuda_check(pcu_transform_update(c, m, T, fu_mu(p), NULL, p->Z, ld, NULL, 0, NULL, 0, NULL, 0, NULL), "pcu_transform_update");
   ecg->ormqr_t += pa_wtime() - t0;
   t0 = pa_wtime();
   pa_cuda_check(pcu_update_z(c, m, T, p->Z, ld, p->P, ld, T, fu_beta1(p), p->Pp, ld, T, fu_beta2(p)), "pcu_update_z");
   if (keep < T) pa_cuda_check(pcu_zero_cols(c, m, T - keep, p->Z + keep, ld), "pcu_zero_cols");
-  pa_cuda_check(pcu_update_xr(c, m, T, p->P, ld, p->AP, ld, fu_alpha(p), p->X, ld, p->R, ld, sm_rr(p)), "pcu_update_xr");
   ecg->gemm_t += pa_wtime() - t0;
   if (reduce) {
     ecg->bs = t1;

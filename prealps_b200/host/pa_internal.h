@@ -22,6 +22,7 @@ int pa_sym_scale(CPLM_Mat_CSR_t* A);
 int pa_kway_parts(const CPLM_Mat_CSR_t* A, int S, int* parts);
 void pa_parts_to_perm(int M, const int* parts, int S, int* posB, int* perm);
 int pa_permute_sym(const CPLM_Mat_CSR_t* A, const int* perm, CPLM_Mat_CSR_t* B);
+int pa_permute_panel(const CPLM_Mat_CSR_t* A, const int* perm, int r0, int r1, CPLM_Mat_CSR_t* B);
 int pa_row_panel(const CPLM_Mat_CSR_t* A, int r0, int r1, CPLM_Mat_CSR_t* B);
 int pa_col_block_pos(const CPLM_Mat_CSR_t* A, const int* rowPos, int S, int** colPos_out, int* n_out);
 int pa_comm_dep(const int* colPos, int m, int S, int lo, int hi, int** dep_out, int* ndep);
@@ -70,6 +71,7 @@ pcu_ctx* pa_ctx(void);                          /* creates the context on first 
 void pa_cuda_check(int rc, const char* what);   /* aborts with pcu_last_error() */
 int pa_is_device_block(const CPLM_Mat_Dense_t* X);
 /* sum n doubles that live on the device across processes (no-op for one process) */
+double pa_sum_over_subdomains(const double* part_local);
 void pa_allreduce_dev(double* dbuf, int n, double* comm_t);
 double pa_wtime(void);
 

@@ -67,6 +67,28 @@ int preAlps_b200_InitNccl(int nranks, int rank, const void* id128) {
 
 int pa_is_device_block(const CPLM_Mat_Dense_t* X) { return pcu_ptr_is_device(X->val); }
 
+/* sum over ALL subdomains, in subdomain order, of one number per local subdomain (NCCL transport): every process fills
+ * its own slots of a zeroed S-vector, the all-reduce adds zeros to them (exact), and everybody adds the S numbers in the
+ * same order -- the order in which the reference's ranks are summed by the MPI shim of the golden runs.  The result does
+ * not depend on the number of GPUs (a scalar all-reduce does: its tree changes the last bit of ||b||). */
+double pa_sum_over_subdomains(const double* part_local) {
+  pa_state_t* g = &pa_g;
+  pcu_ctx* c = pa_ctx();
+  const int S = g->S;
+  double* h = (double*)pa_xcalloc((size_t)S, sizeof(double));
+  for (int s = g->s_lo; s < g->s_hi; ++s) h[s] = part_local[s - g->s_lo];
+  double* d = (double*)pcu_malloc(c, sizeof(double) * (size_t)S);
+  if (!d) CPLM_Abort("device allocation failed: %s", pcu_last_error());
+  pa_cuda_check(pcu_h2d(c, d, h, sizeof(double) * (size_t)S), "pcu_h2d");
+  pa_cuda_check(pcu_allreduce_sum(c, d, S), "pcu_allreduce_sum");
+  pa_cuda_check(pcu_d2h(c, h, d, sizeof(double) * (size_t)S), "pcu_d2h");
+  pcu_free(c, d);
+  double sum = 0.0;
+  for (int s = 0; s < S; ++s) sum += h[s];
+  free(h);
+  return sum;
+}
+
 void pa_allreduce_dev(double* dbuf, int n, double* comm_t) {
   if (pa_g.nproc <= 1 || pa_g.xport == PA_XPORT_NONE) return;
   const double t0 = pa_wtime();
@@ -212,7 +234,13 @@ static int partition_global(CPLM_Mat_CSR_t* G, int S, int s_lo, int s_hi, int sc
   PA_LAP("symmetric max-scaling");
   int* parts = (int*)pa_xmalloc(sizeof(int) * (size_t)M);
   if (parts_in) memcpy(parts, parts_in, sizeof(int) * (size_t)M);
-  else if (pa_kway_parts(G, S, parts)) CPLM_Abort("METIS k-way partitioning failed");
+  else if (g->xport == PA_XPORT_NCCL && g->nproc > 1) {
+    /* one partition for everybody, like the reference (rank 0 partitions and ships the panels, ref: operator.c:54-121):
+     * process 0 runs METIS, the others receive parts[] -- N concurrent copies of the same serial partitioning took 9.5 s
+     * at N = 8 against 1.9 s alone, and nothing checked that they agreed */
+    if (g->rank == 0 && pa_kway_parts(G, S, parts)) CPLM_Abort("METIS k-way partitioning failed");
+    pa_cuda_check(pcu_bcast_ints(pa_ctx(), parts, M, 0), "pcu_bcast_ints");
+  } else if (pa_kway_parts(G, S, parts)) CPLM_Abort("METIS k-way partitioning failed");
   PA_LAP("METIS k-way partition");
   g->rowPos = (int*)pa_xmalloc(sizeof(int) * ((size_t)S + 1));
   g->nrowPos = S + 1;
@@ -221,13 +249,9 @@ static int partition_global(CPLM_Mat_CSR_t* G, int S, int s_lo, int s_hi, int sc
   pa_parts_to_perm(M, parts, S, g->rowPos, g->perm);
   free(parts);
   PA_LAP("parts -> permutation");
-  CPLM_Mat_CSR_t P = CPLM_MatCSRNULL();
-  pa_permute_sym(G, g->perm, &P);
+  pa_permute_panel(G, g->perm, g->rowPos[s_lo], g->rowPos[s_hi], &g->A);  /* = rows of P A P^T, ref: operator.c:86,96-121 */
   CPLM_MatCSRFree(G);
-  PA_LAP("symmetric permutation");
-  pa_row_panel(&P, g->rowPos[s_lo], g->rowPos[s_hi], &g->A);
-  CPLM_MatCSRFree(&P);
-  PA_LAP("row panel");
+  PA_LAP("symmetric permutation of the local rows");
 #undef PA_LAP
   return 0;
 }

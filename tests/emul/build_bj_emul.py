@@ -95,11 +95,6 @@ def build(asan=False):
     return so
 
 
-if __name__ == "__main__":
-    import sys
-    print(build_full() if "--full" in sys.argv else build(asan="--asan" in sys.argv))
-
-
 def build_full():
     """the whole product stack for the emulation: every .cu of libprealps_cuda and the plain-C host layer, as
     tests/_build/emul_lib/{libprealps_cuda,libprealps_b200,libmpishim}.so (same names: the host library finds the emulated
@@ -132,3 +127,8 @@ def build_full():
                           [METIS_A, "-Wl,--exclude-libs=ALL", "-L" + out, "-lprealps_cuda", "-lmpishim", "-Wl,-rpath,$ORIGIN", "-o", so_host,
                            "-lm", "-lpthread"])
     return out
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_full() if "--full" in sys.argv else build(asan="--asan" in sys.argv))

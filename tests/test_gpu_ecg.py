@@ -57,7 +57,12 @@ def test_solve_matches_reference(name):
     sol, hist, info = capi.solve(rhs, t, tol, ortho=ortho, bs_red=1 if adapt else 0)
     assert abs(info.iter - int(g["iter"])) <= 1                       # north_star: iteration count +-1
     n = min(len(hist), len(g["res_hist"]))
-    if adapt:  # ADAPT_BS (-r 1): the same reductions of the block size at the same iterations
+    if adapt and name.endswith("rankdrop"):
+        # the drop happens at the last iteration, on directions of norm 1e-20 ||b||: that a direction is dropped there is
+        # pinned, how many of those noise vectors survive dpstrf's threshold is not (B200: 2, the reference's run: 3)
+        bs = capi.last_block_sizes()[:n]
+        assert np.array_equal(bs[:n - 1], g["bs_hist"][:n - 1]) and 0 < bs[n - 1] < t and g["bs_hist"][n - 1] < t
+    elif adapt:  # ADAPT_BS (-r 1): the same reductions of the block size at the same iterations
         assert np.array_equal(capi.last_block_sizes()[:n], g["bs_hist"][:n])
     # whole history (ADAPT_BS on the elasticity operators: Jacobi SVD here, dgesvd + dormqr in the reference;
     # the numpy restatement differs from the reference by 1.9e-6 at the last iteration)
@@ -296,7 +301,7 @@ def test_full_size_configs_match_the_reference_run(name, record_property):
     assert dev[:10].max() <= 1e-9
     if int(g["bs_red"]) == 0:
         assert info.iter == int(g["iter"])
-        assert dev.max() <= 1e-6   # 10x the largest deviation measured on B200 (profiles/r02_gpu_tests.log)
+        assert dev.max() <= 1e-7   # measured on B200: 1.5e-8 at 128^3, 1.1e-8 at 64^3, 2.0e-9 at 32^3 (profiles/r02_gpu_tests.log)
         assert abs(info.true_relres - float(g["true_relres"])) <= 1e-3 * float(g["true_relres"])
     else:
         assert np.array_equal(capi.last_block_sizes()[:first], np.asarray(g["bs_hist"])[:first])
