@@ -29,7 +29,7 @@ all: $(TARGETS)
 $(OBJ) $(LIB) $(BIN):
 	mkdir -p $@
 
-$(OBJ)/%.o: prealps_b200/csrc/%.cu prealps_b200/csrc/common.cuh prealps_b200/csrc/bj.h prealps_b200/csrc/spmm_kernels.cuh include/prealps_cuda.h | $(OBJ)
+$(OBJ)/%.o: prealps_b200/csrc/%.cu prealps_b200/csrc/common.cuh prealps_b200/csrc/bj.h prealps_b200/csrc/bj_symbolic.h prealps_b200/csrc/spmm_kernels.cuh include/prealps_cuda.h | $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(OBJ)/bj_symbolic.o: prealps_b200/csrc/bj_symbolic.cpp prealps_b200/csrc/bj_symbolic.h | $(OBJ)

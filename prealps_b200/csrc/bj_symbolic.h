@@ -32,11 +32,12 @@ struct Symbolic {
 };
 
 struct SymbolicOptions {
-  int leaf_cols = 32;       // merge a whole elimination subtree into one dense supernode if it has <= this many columns
+  int leaf_cols = 48;       // merge a whole elimination subtree into one dense supernode if it has <= this many columns
   double relax_zero = 0.2;  // merge a last child into its parent if the fraction of explicit zeros stays below this
   int relax_small = 16;     // ... or if both are narrower than this
-  int relax_big_cols = 1 << 30;  // merged supernodes wider than this are held to relax_big instead: a wide supernode streams
-  double relax_big = 0.2;        // at full rate anyway, its explicit zeros are pure extra traffic
+  int relax_big_cols = 256;      // merged supernodes wider than this are held to relax_big instead: a wide supernode streams
+  double relax_big = 0.05;       // at full rate anyway, its explicit zeros are pure extra traffic (measured on B200, 8 blocks of
+                                 // 64^3: stored bytes 19.19 -> 18.34 GB, apply 3.76 -> 3.69 ms; profiles/r02_candidates_ab.md)
   bool use_metis = true;    // false: natural ordering (tests)
 };
 

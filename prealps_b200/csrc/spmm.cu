@@ -21,14 +21,30 @@
 
 namespace {
 
-template <int T>
-void launch_bulk(const SpmmArgs& a, int nblk, bool wide, bool halo, cudaStream_t st) {
+template <int T, int CAPN, int CAPR>
+void launch_bulk_cap(const SpmmArgs& a, int nblk, bool wide, bool halo, cudaStream_t st) {
   if (wide) {
-    if (halo) spmm_bulk_kernel<T, 4, true><<<nblk, kThreads, 0, st>>>(a);
-    else spmm_bulk_kernel<T, 4, false><<<nblk, kThreads, 0, st>>>(a);
+    if (halo) spmm_bulk_kernel<T, 4, true, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
+    else spmm_bulk_kernel<T, 4, false, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
   } else {
-    if (halo) spmm_bulk_kernel<T, 2, true><<<nblk, kThreads, 0, st>>>(a);
-    else spmm_bulk_kernel<T, 2, false><<<nblk, kThreads, 0, st>>>(a);
+    if (halo) spmm_bulk_kernel<T, 2, true, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
+    else spmm_bulk_kernel<T, 2, false, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
+  }
+}
+
+// shape of the row blocks of the bulk-staging kernel: index into kBulkShapes (PREALPS_SPMM_SHAPE, read at creation)
+constexpr int kNumBulkShapes = 5;
+constexpr int kBulkNnz[kNumBulkShapes] = {1536, 768, 1024, 2048, 3072};
+constexpr int kBulkRows[kNumBulkShapes] = {128, 64, 96, 192, 256};
+
+template <int T>
+void launch_bulk(const SpmmArgs& a, int nblk, bool wide, bool halo, int shape, cudaStream_t st) {
+  switch (shape) {
+    case 1: launch_bulk_cap<T, kBulkNnz[1], kBulkRows[1]>(a, nblk, wide, halo, st); break;
+    case 2: launch_bulk_cap<T, kBulkNnz[2], kBulkRows[2]>(a, nblk, wide, halo, st); break;
+    case 3: launch_bulk_cap<T, kBulkNnz[3], kBulkRows[3]>(a, nblk, wide, halo, st); break;
+    case 4: launch_bulk_cap<T, kBulkNnz[4], kBulkRows[4]>(a, nblk, wide, halo, st); break;
+    default: launch_bulk_cap<T, kBulkNnz[0], kBulkRows[0]>(a, nblk, wide, halo, st); break;
   }
 }
 
@@ -39,6 +55,7 @@ struct CsrDev {
   double* val = nullptr;
   int4* blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
   int nblk[2] = {0, 0};
+  int bulk_shape = 0;                 // blk[0] was built with kBulkNnz / kBulkRows[bulk_shape]
   int64_t nnz = 0;
   bool fits0 = true;  // every shape-0 row block fits the staging buffer (spmm_bulk_kernel needs that)
 };
@@ -46,12 +63,22 @@ struct CsrDev {
 int upload_csr(int m, const int* rowPtr, const int* colInd, const double* val, CsrDev* d) {
   d->nnz = rowPtr[m];
   std::vector<int4> blk[2];
+  if (const char* e = getenv("PREALPS_SPMM_SHAPE")) d->bulk_shape = std::max(0, std::min(kNumBulkShapes - 1, atoi(e)));
   for (int sh = 0; sh < 2; ++sh) {
-    build_row_blocks(m, rowPtr, sh, &blk[sh]);
+    if (sh == 0) build_row_blocks_cap(m, rowPtr, kBulkRows[d->bulk_shape], kBulkNnz[d->bulk_shape], &blk[sh]);
+    else build_row_blocks(m, rowPtr, sh, &blk[sh]);
     d->nblk[sh] = (int)blk[sh].size();
   }
   for (const int4& b : blk[0])
-    if (b.w - b.z > kShapeNnz[0]) d->fits0 = false;
+    if (b.w - b.z > kBulkNnz[d->bulk_shape]) d->fits0 = false;
+  if (d->bulk_shape != 0 && !d->fits0) {  // spmm_kernel's staging buffers are sized for the default shape
+    d->bulk_shape = 0;
+    build_row_blocks(m, rowPtr, 0, &blk[0]);
+    d->nblk[0] = (int)blk[0].size();
+    d->fits0 = true;
+    for (const int4& b : blk[0])
+      if (b.w - b.z > kShapeNnz[0]) d->fits0 = false;
+  }
   PCU_CUDA(cudaMalloc(&d->rowPtr, sizeof(int) * (size_t)(m + 1)));
   // 16 bytes of slack: spmm_bulk_kernel rounds the size of its bulk copies up to a multiple of 16
   PCU_CUDA(cudaMalloc(&d->colInd, sizeof(int) * (size_t)(d->nnz + 4)));
@@ -251,14 +278,17 @@ static int launch_spmm(pcu_spmm* op, const CsrDev& A, const double* X, int ldx, 
   // 256-bit accesses need 32-byte aligned rows (the halo buffer has ld = t). They pay for short rows, where the
   // per-row instructions dominate and twice the rows per warp halves them (7-point: 126 -> 112 us at t = 8); with 27
   // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
-  const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
-                    ((uintptr_t)op->d_halo % 32 == 0) && A.nnz <= 12 * (int64_t)op->m;
+  const bool wide_ok = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
+                       ((uintptr_t)op->d_halo % 32 == 0);
+  static const int force_wide = getenv("PREALPS_SPMM_WIDE") ? atoi(getenv("PREALPS_SPMM_WIDE")) : -1;
+  const bool wide = wide_ok && (force_wide >= 0 ? force_wide != 0 : A.nnz <= 12 * (int64_t)op->m);
   const bool bulk = op->bulk && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
+  PCU_CHECK(bulk || A.bulk_shape == 0 || t <= 4, "pcu_spmm_apply: PREALPS_SPMM_SHAPE needs the bulk-staging kernel (t = 8, 16, 32, aligned blocks)");
   if (bulk) {
     const bool halo = (&A == &op->A) && op->nhalo > 0;  // the local part of the overlapped product has no column >= m
-    if (t == 8) launch_bulk<8>(a, nblk, wide, halo, c->stream);
-    else if (t == 16) launch_bulk<16>(a, nblk, wide, halo, c->stream);
-    else launch_bulk<32>(a, nblk, wide, halo, c->stream);
+    if (t == 8) launch_bulk<8>(a, nblk, wide, halo, A.bulk_shape, c->stream);
+    else if (t == 16) launch_bulk<16>(a, nblk, wide, halo, A.bulk_shape, c->stream);
+    else launch_bulk<32>(a, nblk, wide, halo, A.bulk_shape, c->stream);
   } else if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {

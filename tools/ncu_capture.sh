@@ -11,8 +11,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'sweep|assemb
 # 2. DRAM traffic of every launch of one block-Jacobi apply
 python tools/profile_apply.py 128 1 1 > $out/p_bj.log 2>&1 || { echo "apply run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'sweep|assemble' \
-    -c 400 --csv --log-file $out/traffic_bj.csv python tools/profile_apply.py 128 1 1 > $out/ncu_bj.log 2>&1
+    -c 600 --csv --log-file $out/traffic_bj.csv python tools/profile_apply.py 128 1 1 > $out/ncu_bj.log 2>&1
 # 3. full capture of the forward sweep of three big levels (launch 10-12 of sweep_kernel)
-ncu --set full --clock-control none --import-source on -k regex:'sweep_kernel' -s 10 -c 3 -o $out/r01_prof_sweep_final -f \
+ncu --set full --clock-control none --import-source on -k regex:'sweep_kernel' -s 10 -c 3 -o $out/r02_prof_sweep -f \
     python tools/profile_apply.py 128 1 1 > $out/ncu_sw.log 2>&1
 ls -la $out/*.csv $out/*.ncu-rep
