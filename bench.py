@@ -256,6 +256,7 @@ def main():
     torch.cuda.set_device(local)
     capi.lib.preAlps_b200_SetDevice(local)
     dist = None
+    t_nccl = 0.0
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -267,7 +268,9 @@ def main():
         uid = uid.cuda()
         dist.broadcast(uid, 0)
         raw = bytes(uid.cpu().tolist())
-        assert capi.lib.preAlps_b200_InitNccl(world, rank, raw) == 0
+        t_nccl = time.time()
+        assert capi.lib.preAlps_b200_InitNccl(world, rank, raw) == 0   # includes NCCL's first collective (channel set-up)
+        t_nccl = time.time() - t_nccl
 
     def barrier():
         torch.cuda.synchronize()
@@ -376,7 +379,7 @@ def main():
             "roofline": roofline,
             "kernels": kern,
             "cpu_baseline": cpu,
-            "setup": {"partition_s": t_part, "total_s": t_setup, "bj_analysis_s": capi.stat("bj_analysis_s"),
+            "setup": {"nccl_init_s": t_nccl, "operator_build_s": t_part, "total_s": t_setup, "bj_analysis_s": capi.stat("bj_analysis_s"),
                       "bj_factor_s": capi.stat("bj_factor_s"), "bj_nnz_exact": capi.stat("bj_nnz_exact"),
                       "bj_nnz_stored": capi.stat("bj_nnz_stored"), "bj_supernodes": capi.stat("bj_supernodes"),
                       "bj_levels": capi.stat("bj_levels"), "rows_per_gpu": m},

@@ -543,7 +543,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   bj->bwd_unit_ptr.assign(nlev + 1, 0);
   std::vector<std::vector<PackTask>> pk_f(nlev), pk_b(nlev);
   long long fdoubles = 0, bdoubles = 0;
-  const int kSplitK = 512;  // panels at least this long get a whole CTA (split-K over its 8 warps)
+  const int kSplitK = 512;  // without level-adaptive cuts (PREALPS_BJ_NOCHUNK): panels at least this long get a whole CTA
   bj->fwd_tiny0.assign(nlev, 0); bj->fwd_tinyn.assign(nlev, 0);
   bj->bwd_tiny0.assign(nlev, 0); bj->bwd_tinyn.assign(nlev, 0);
   bj->fwd_tinys.assign(nlev, 0); bj->bwd_tinys.assign(nlev, 0);
@@ -552,10 +552,12 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   auto make_units = [&](std::vector<int>& klen_of, int first, int count_all, std::vector<WorkUnit>& units, int* tiny0,
                         int* tinyn, int* tinys) {
     int count = count_all;
+    const size_t u_begin = units.size();
     if (use_tiny) while (count > 0 && klen_of[first + count - 1] <= kTinyK) --count;
     // a handful of short panels next to longer ones ride along in the main launch (one warp each) instead of
     // costing the level another one or two launches
-    if (count > 0 && count_all - count < kTinyFold) count = count_all;
+    static const int tiny_fold = getenv("PREALPS_BJ_TINYFOLD") ? atoi(getenv("PREALPS_BJ_TINYFOLD")) : kTinyFold;
+    if (count > 0 && count_all - count < tiny_fold) count = count_all;
     *tiny0 = first + count;
     *tinyn = count_all - count;
     int cs = count_all;
@@ -574,10 +576,14 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     int split_kb = kSplitK / 4, chunk_kb = 1 << 30;
     if (use_chunks) {
       const int q = (int)std::max<long long>(16, (level_kb + kWarpSlots - 1) / kWarpSlots);
-      split_kb = std::min(kSplitK / 4, std::max(32, 4 * q));
-      // a slice = one CTA slot's share of the level (8 q).  Smaller slices, i.e. several waves of CTAs per level, are
-      // slower: 0.875 / 0.917 / 0.958 ms for the apply of one 64^3 block with 8 q / 4 q / 2 q (more partial sums to combine)
-      const int per_unit = getenv("PREALPS_BJ_CHUNKQ") ? atoi(getenv("PREALPS_BJ_CHUNKQ")) : 8;
+      // a panel gets a whole CTA from 3/4 of a warp's share of the level on (32 .. 256 k-blocks).  Measured on B200 (apply, ms,
+      // one 64^3 block / eight): fixed 128 k-blocks 0.785 / 3.510; 64: 0.744 / 3.598; 256: 0.849 / 3.484; this rule 0.747 / 3.489
+      static const int split_a = getenv("PREALPS_BJ_SPLITA") ? atoi(getenv("PREALPS_BJ_SPLITA")) : 6;
+      split_kb = std::min(256, std::max(32, (q * split_a / 8 + 15) & ~15));
+      // a slice = 10 q: a level's long panels then make ONE wave of CTAs (2 x 148 slots).  Measured, apply of one 64^3
+      // block: 0.958 / 0.917 / 0.883 / 0.810 / 0.820 / 0.849 ms with 2 / 4 / 8 / 10 / 12 / 16 q -- smaller slices mean more
+      // partial sums and a second, partly filled wave that costs as much as a full one; 8 blocks per GPU: no difference
+      const int per_unit = getenv("PREALPS_BJ_CHUNKQ") ? atoi(getenv("PREALPS_BJ_CHUNKQ")) : 10;
       chunk_kb = std::max(kChunkMinKB, (per_unit * q + 7) & ~7);
     }
     int nlong = 0;
@@ -598,6 +604,17 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     bj->scratch_slots = std::max(bj->scratch_slots, slots);
     bj->ncounters = std::max(bj->ncounters, ctrs);
     while (i < count) { const int c = std::min(8, count - i); units.push_back({first + i, c, 0, 0, 0, 0, 1, 0, 0, 0}); i += c; }
+    // CTAs are dispatched in unit order: longest first by TIME, not by panel length.  A CTA whose 8 warps each stream a
+    // whole panel of just under split_kb k-blocks runs as long as a CTA that shares a panel 8 times as long; left at
+    // the end of the list (they were, the list being sorted by panel length) those groups were the tail of every level.
+    if (getenv("PREALPS_BJ_NOLPT") == nullptr) {
+      auto cost = [&](const WorkUnit& u) {
+        if (u.split == 2) return (u.kb1 - u.kb0 + 7) / 8;
+        if (u.split == 1) return (klen_of[u.first] / 4 + 7) / 8;
+        return klen_of[u.first] / 4;  // the first panel of a group is its longest
+      };
+      std::stable_sort(units.begin() + u_begin, units.end(), [&](const WorkUnit& a, const WorkUnit& b) { return cost(a) > cost(b); });
+    }
   };
   for (int l = 0; l < nlev; ++l) {
     // forward

@@ -251,6 +251,14 @@ int pcu_ctx_init_nccl(pcu_ctx* c, int nranks, int rank, const void* id128) {
   memcpy(&id, id128, PCU_NCCL_ID_BYTES);
   PCU_CUDA(cudaSetDevice(c->device));
   PCU_NCCL(g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank));
+  // NCCL sets its channels up on the first collective (8 ranks: ~8 s, which round 1 had mistaken for eight METIS runs
+  // competing for the host): pay for it here, once, where it can be told apart from the operator build
+  double* d = nullptr;
+  PCU_CUDA(cudaMalloc(&d, sizeof(double)));
+  PCU_CUDA(cudaMemsetAsync(d, 0, sizeof(double), c->stream));
+  PCU_NCCL(g_nccl.AllReduce(d, d, 1, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream));
+  PCU_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
   return 0;
 }
 int pcu_comm_size(pcu_ctx* c) { return c->nranks; }
