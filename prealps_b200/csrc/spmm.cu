@@ -21,30 +21,16 @@
 
 namespace {
 
-template <int T, int CAPN, int CAPR>
-void launch_bulk_cap(const SpmmArgs& a, int nblk, bool wide, bool halo, cudaStream_t st) {
-  if (wide) {
-    if (halo) spmm_bulk_kernel<T, 4, true, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
-    else spmm_bulk_kernel<T, 4, false, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
-  } else {
-    if (halo) spmm_bulk_kernel<T, 2, true, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
-    else spmm_bulk_kernel<T, 2, false, CAPN, CAPR><<<nblk, kThreads, 0, st>>>(a);
-  }
-}
-
-// shape of the row blocks of the bulk-staging kernel: index into kBulkShapes (PREALPS_SPMM_SHAPE, read at creation)
-constexpr int kNumBulkShapes = 5;
-constexpr int kBulkNnz[kNumBulkShapes] = {1536, 768, 1024, 2048, 3072};
-constexpr int kBulkRows[kNumBulkShapes] = {128, 64, 96, 192, 256};
-
+// Row-block shapes (entries / rows per CTA) of 768/64, 1024/96, 2048/192 and 3072/256 and the 4-columns-per-lane mapping for
+// long rows were measured against this one on B200 and lost or tied (profiles/r02_spmm_shapes_rejected.md)
 template <int T>
-void launch_bulk(const SpmmArgs& a, int nblk, bool wide, bool halo, int shape, cudaStream_t st) {
-  switch (shape) {
-    case 1: launch_bulk_cap<T, kBulkNnz[1], kBulkRows[1]>(a, nblk, wide, halo, st); break;
-    case 2: launch_bulk_cap<T, kBulkNnz[2], kBulkRows[2]>(a, nblk, wide, halo, st); break;
-    case 3: launch_bulk_cap<T, kBulkNnz[3], kBulkRows[3]>(a, nblk, wide, halo, st); break;
-    case 4: launch_bulk_cap<T, kBulkNnz[4], kBulkRows[4]>(a, nblk, wide, halo, st); break;
-    default: launch_bulk_cap<T, kBulkNnz[0], kBulkRows[0]>(a, nblk, wide, halo, st); break;
+void launch_bulk(const SpmmArgs& a, int nblk, bool wide, bool halo, cudaStream_t st) {
+  if (wide) {
+    if (halo) spmm_bulk_kernel<T, 4, true><<<nblk, kThreads, 0, st>>>(a);
+    else spmm_bulk_kernel<T, 4, false><<<nblk, kThreads, 0, st>>>(a);
+  } else {
+    if (halo) spmm_bulk_kernel<T, 2, true><<<nblk, kThreads, 0, st>>>(a);
+    else spmm_bulk_kernel<T, 2, false><<<nblk, kThreads, 0, st>>>(a);
   }
 }
 
@@ -55,7 +41,6 @@ struct CsrDev {
   double* val = nullptr;
   int4* blk[2] = {nullptr, nullptr};  // row blocks of shape kShapeRows/kShapeNnz[i]
   int nblk[2] = {0, 0};
-  int bulk_shape = 0;                 // blk[0] was built with kBulkNnz / kBulkRows[bulk_shape]
   int64_t nnz = 0;
   bool fits0 = true;  // every shape-0 row block fits the staging buffer (spmm_bulk_kernel needs that)
 };
@@ -63,22 +48,12 @@ struct CsrDev {
 int upload_csr(int m, const int* rowPtr, const int* colInd, const double* val, CsrDev* d) {
   d->nnz = rowPtr[m];
   std::vector<int4> blk[2];
-  if (const char* e = getenv("PREALPS_SPMM_SHAPE")) d->bulk_shape = std::max(0, std::min(kNumBulkShapes - 1, atoi(e)));
   for (int sh = 0; sh < 2; ++sh) {
-    if (sh == 0) build_row_blocks_cap(m, rowPtr, kBulkRows[d->bulk_shape], kBulkNnz[d->bulk_shape], &blk[sh]);
-    else build_row_blocks(m, rowPtr, sh, &blk[sh]);
+    build_row_blocks(m, rowPtr, sh, &blk[sh]);
     d->nblk[sh] = (int)blk[sh].size();
   }
   for (const int4& b : blk[0])
-    if (b.w - b.z > kBulkNnz[d->bulk_shape]) d->fits0 = false;
-  if (d->bulk_shape != 0 && !d->fits0) {  // spmm_kernel's staging buffers are sized for the default shape
-    d->bulk_shape = 0;
-    build_row_blocks(m, rowPtr, 0, &blk[0]);
-    d->nblk[0] = (int)blk[0].size();
-    d->fits0 = true;
-    for (const int4& b : blk[0])
-      if (b.w - b.z > kShapeNnz[0]) d->fits0 = false;
-  }
+    if (b.w - b.z > kShapeNnz[0]) d->fits0 = false;
   PCU_CUDA(cudaMalloc(&d->rowPtr, sizeof(int) * (size_t)(m + 1)));
   // 16 bytes of slack: spmm_bulk_kernel rounds the size of its bulk copies up to a multiple of 16
   PCU_CUDA(cudaMalloc(&d->colInd, sizeof(int) * (size_t)(d->nnz + 4)));
@@ -106,7 +81,7 @@ struct pcu_spmm {
   int64_t nnz = 0;
   CsrDev A;           // the local row panel, columns >= m read the halo buffer
   bool bulk = true;   // spmm_bulk_kernel (cp.async.bulk staging) from t = 8 up; PREALPS_SPMM_BULK=0 keeps spmm_kernel (A/B runs)
-  // PREALPS_SPMM_OVERLAP=1 and nhalo > 0: the panel split into its entries with column < m (Aloc, same rows) and the halo
+  // nhalo > 0 (unless PREALPS_SPMM_OVERLAP=0): the panel split into its entries with column < m (Aloc, same rows) and the halo
   // entries of the boundary rows; the halo exchange then runs on comm_stream next to the local kernel
   bool overlap = false;
   CsrDev Aloc;
@@ -160,7 +135,11 @@ int pcu_spmm_create(pcu_ctx* ctx, int m, int nhalo, const int* rowPtr, const int
               colInd[p], (long long)p);
   if (upload_csr(m, rowPtr, colInd, val, &op->A)) return 1;
   if (const char* e = getenv("PREALPS_SPMM_BULK")) op->bulk = atoi(e) != 0;
-  if (getenv("PREALPS_SPMM_OVERLAP") != nullptr && nhalo > 0) {
+  // the halo exchange overlapped with the local part of the product, like the reference's MPI_Isend / diagonal block /
+  // MPI_Irecv (ref: cplm_v0_matmult_v2.c:182-276): default whenever there is a halo; PREALPS_SPMM_OVERLAP=0 serialises
+  // pack -> exchange -> product (measured on 8 B200: SpMM 58.3 -> 54.5 us, the iteration unchanged at 1.11 ms)
+  const char* ov = getenv("PREALPS_SPMM_OVERLAP");
+  if (nhalo > 0 && !(ov && atoi(ov) == 0)) {
     // split: Aloc keeps the entries with column < m of every row; (brow, hptr, hcol, hval) the others
     std::vector<int> lrp, lci, brow, hptr, hcol;
     std::vector<double> lv, hv;
@@ -278,17 +257,14 @@ static int launch_spmm(pcu_spmm* op, const CsrDev& A, const double* X, int ldx, 
   // 256-bit accesses need 32-byte aligned rows (the halo buffer has ld = t). They pay for short rows, where the
   // per-row instructions dominate and twice the rows per warp halves them (7-point: 126 -> 112 us at t = 8); with 27
   // entries per row a block holds fewer rows than the CTA has lane groups and the narrow mapping is faster.
-  const bool wide_ok = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
-                       ((uintptr_t)op->d_halo % 32 == 0);
-  static const int force_wide = getenv("PREALPS_SPMM_WIDE") ? atoi(getenv("PREALPS_SPMM_WIDE")) : -1;
-  const bool wide = wide_ok && (force_wide >= 0 ? force_wide != 0 : A.nnz <= 12 * (int64_t)op->m);
+  const bool wide = (t % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)X % 32 == 0) && ((uintptr_t)Y % 32 == 0) &&
+                    ((uintptr_t)op->d_halo % 32 == 0) && A.nnz <= 12 * (int64_t)op->m;
   const bool bulk = op->bulk && A.fits0 && aligned && pow2 && t >= 8 && ldx == t;
-  PCU_CHECK(bulk || A.bulk_shape == 0 || t <= 4, "pcu_spmm_apply: PREALPS_SPMM_SHAPE needs the bulk-staging kernel (t = 8, 16, 32, aligned blocks)");
   if (bulk) {
     const bool halo = (&A == &op->A) && op->nhalo > 0;  // the local part of the overlapped product has no column >= m
-    if (t == 8) launch_bulk<8>(a, nblk, wide, halo, A.bulk_shape, c->stream);
-    else if (t == 16) launch_bulk<16>(a, nblk, wide, halo, A.bulk_shape, c->stream);
-    else launch_bulk<32>(a, nblk, wide, halo, A.bulk_shape, c->stream);
+    if (t == 8) launch_bulk<8>(a, nblk, wide, halo, c->stream);
+    else if (t == 16) launch_bulk<16>(a, nblk, wide, halo, c->stream);
+    else launch_bulk<32>(a, nblk, wide, halo, c->stream);
   } else if (t == 1) spmm_kernel<1, 1><<<nblk, kThreads, 0, c->stream>>>(a);
   else if (aligned && pow2) {
     switch (t) {
@@ -323,11 +299,10 @@ int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, i
   return launch_spmm(op, op->A, X, ldx, Y, ldy, t);
 }
 
-// halo exchange over NCCL + product.  Default: one after the other on the library stream.  PREALPS_SPMM_OVERLAP=1 (opt-in,
-// written after the last GPU session of round 1, not measured yet): the exchange runs on a second stream while the local
-// part of the product (entries with column < m: > 99 % of them) runs on the library stream, then halo_add_kernel adds
-// the halo entries of the boundary rows -- what the reference does with MPI_Isend / diagonal block / MPI_Irecv
-// (ref: utils/cplm_v0/cplm_v0_matmult_v2.c:182-276).
+// halo exchange over NCCL + product: the exchange (pack + grouped ncclSend / ncclRecv) runs on a second stream while the
+// local part of the product (entries with column < m: > 99 % of them) runs on the library stream, then halo_add_kernel
+// adds the halo entries of the boundary rows -- what the reference does with MPI_Isend / diagonal block / MPI_Irecv
+// (ref: utils/cplm_v0/cplm_v0_matmult_v2.c:182-276).  PREALPS_SPMM_OVERLAP=0 at creation: one after the other.
 int pcu_spmm_apply_exchange(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, int t) {
   PCU_CHECK(op && X && Y && t >= 1 && t <= 32, "pcu_spmm_apply_exchange: bad arguments");
   PCU_CHECK(X != Y, "pcu_spmm_apply_exchange: X and Y must not alias");

@@ -183,17 +183,16 @@ inline void pcu_trap() { std::abort(); }
 // and the sizes rounded up (the device arrays carry 16 bytes of slack at the end).  HALO = false (no column >= m: one
 // process, or the local part of the overlapped product) drops the "block row or halo row" select, so the row phase is
 // LDS + LDS + IMAD.WIDE + LDG + CPL DFMA per entry.  Needs ldx == T and every row block within the staging capacity.
-// CAPN / CAPR: staging capacity (entries / rows) of the row blocks this instantiation is launched on
-template <int T, int CPL, bool HALO, int CAPN = kShapeNnz[0], int CAPR = kShapeRows[0]>
+template <int T, int CPL, bool HALO>
 __global__ void __launch_bounds__(kThreads, CPL == 4 ? 6 : 8) spmm_bulk_kernel(SpmmArgs a) {  // <= 40 / 32 registers, no spills
 
   static_assert(CPL == 2 || CPL == 4, "lanes own 2 or 4 adjacent columns");
   constexpr int G = T / CPL;
   constexpr int NG = kThreads / G;
-  constexpr int kCap = CAPN;
+  constexpr int kCap = kShapeNnz[0];
   __shared__ __align__(16) int s_col[kCap + 8];
   __shared__ __align__(16) double s_val[kCap + 4];
-  __shared__ int s_rp[CAPR + 1];
+  __shared__ int s_rp[kShapeRows[0] + 1];
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int4 d = __ldg(a.blk + blockIdx.x);
@@ -335,18 +334,6 @@ __global__ void __launch_bounds__(kThreads) halo_add_kernel(int nb, const int* _
     }
     if (lig < t) y[lig] = acc0;
     if (lig + 16 < t) y[lig + 16] = acc1;
-  }
-}
-
-// row blocks of at most `rows` rows and `nnz` entries; an over-long row gets a block of its own
-inline void build_row_blocks_cap(int m, const int* rowPtr, int rows, int nnz, std::vector<int4>* blk) {
-  blk->clear();
-  for (int r = 0; r < m;) {
-    int e = r;
-    while (e < m && e - r < rows && rowPtr[e + 1] - rowPtr[r] <= nnz) ++e;
-    if (e == r) e = r + 1;
-    blk->push_back(make_int4(r, e, rowPtr[r], rowPtr[e]));
-    r = e;
   }
 }
 

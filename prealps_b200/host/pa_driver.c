@@ -214,7 +214,7 @@ int preAlps_b200_BenchKernel(int what, int t, int reps, int flush_l2, float* ms_
     if (flush_l2) pa_cuda_check(pcu_flush_l2(c), "pcu_flush_l2");
     pcu_timer_start(c, 2);
     if (what == 0) {
-      if (g->nproc > 1 && g->xport == PA_XPORT_NCCL && getenv("PREALPS_SPMM_OVERLAP")) {
+      if (g->nproc > 1 && g->xport == PA_XPORT_NCCL) {
         pa_cuda_check(pcu_spmm_apply_exchange(g->spmm, P, ld, AP, ld, t), "pcu_spmm_apply_exchange");
       } else {
         if (g->nproc > 1 && g->xport == PA_XPORT_NCCL) pa_cuda_check(pcu_spmm_halo_exchange(g->spmm, P, ld, t), "halo");

@@ -578,8 +578,8 @@ int preAlps_BlockOperator(CPLM_Mat_Dense_t* X, CPLM_Mat_Dense_t* AX) {
   double* y; int ldy;
   if (dev_out) { y = AX->val; ldy = AX->info.lda; }
   else { pa_ensure_stage((size_t)g->m * t + 8); y = g->d_stage_out; ldy = t; if (!dev_in) x = g->d_stage_in; }
-  if (g->nproc > 1 && g->xport == PA_XPORT_NCCL && getenv("PREALPS_SPMM_OVERLAP")) {
-    /* exchange + product in one call, overlapped by the library (opt-in until it has been measured) */
+  if (g->nproc > 1 && g->xport == PA_XPORT_NCCL) {
+    /* exchange + product in one call: the library overlaps the exchange with the local part of the product */
     pa_cuda_check(pcu_spmm_apply_exchange(g->spmm, x, ldx, y, ldy, t), "pcu_spmm_apply_exchange");
   } else {
     halo_exchange(x, ldx, t);
