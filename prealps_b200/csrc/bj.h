@@ -7,13 +7,22 @@
 //   streaming products without any intra-supernode dependency:
 //     forward   [y_s ; u_s] = M_s b_s          (u_s = contribution to the ancestors)
 //     backward  x_s = M_s^T [y_s ; -x_below]
-//   M_s is stored twice, cut into 32-row panels of klen steps (klen a multiple of 4):
-//     fwd panel p of s: rows [32p, 32p+32) of M_s,   steps k = columns of M_s
-//     bwd panel q of s: rows [32q, 32q+32) of M_s^T, steps k = rows 32q.. of M_s (lower part negated)
+//   M_s is cut into 32-row slices ("panels") of klen steps (klen a multiple of 4); the rows below the diagonal block
+//   are stored negated:
+//     fwd panel p of s: rows [32p, 32p+32) of M_s, steps k = columns [0, min(w, 32p+32)) of M_s; produces y_s and -u_s
+//     bwd panel q of s: columns [32q, 32q+32) of M_s = k-blocks [8q, 8q+8) of every fwd panel p >= q, walked tile by
+//                       tile (32 rows x 32 columns = 8 KB contiguous); steps k = rows 32q.. of M_s
 //   A panel is a sequence of k-blocks (4 steps, 128 doubles = 1 KB) stored in the A-fragment order of
 //   mma.sync.m8n8k4.f64: data[kb*128 + lane*4 + rg] = panel(8*rg + lane/4, 4*kb + lane%4).  A warp streams a
 //   panel with perfectly coalesced 1 KB reads (32 B per lane) and multiplies it with the t-wide input rows
-//   (B fragment: one shared-memory double per lane and k-block) on the FP64 tensor cores.
+//   (B fragment: one shared-memory double per lane and k-block) on the FP64 tensor cores.  The backward sweep reads the
+//   same k-blocks with a permuted lane -> address map that yields the A fragments of M_s^T directly (bj_solve.cu:
+//   bwd_lane_offset), so ONE copy of the factor serves both sweeps.
+//   The panels of a supernode are contiguous, slice after slice: slice p starts panel_cum(w, p) doubles after the
+//   supernode's first one, so the backward sweep needs no per-slice offset table.
+//   When memory allows (bj_factor.cu: tcopy) the factor also keeps M_s^T cut into its own 32-row slices (bwd_data): the
+//   backward sweep then streams contiguous panels like the forward one, ~10 % faster than the strided 8 KB tiles of the
+//   single copy on B200 (same bytes; measured, profiles/r02_single_copy_factor.md).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -21,6 +30,13 @@
 #include "common.cuh"
 
 namespace pcu {
+
+// doubles stored in front of slice p of a supernode of width w: slices p' < p hold min(W4, 8p'+8) k-blocks of 128
+// doubles each, W4 = ceil(w / 4)
+__host__ __device__ inline long long panel_cum(int w, int p) {
+  const int W4 = (w + 3) >> 2, pt = W4 >> 3, m = p < pt ? p : pt;
+  return 128ll * (4ll * m * (m + 1) + (long long)(p > pt ? p - pt : 0) * W4);
+}
 
 struct FwdPanel {      // one 32-row slice of M_s
   long long off;       // offset (doubles) into fwd_data
@@ -32,11 +48,13 @@ struct FwdPanel {      // one 32-row slice of M_s
   int pad_;
 };
 
-struct BwdPanel {      // one 32-row slice of M_s^T
-  long long off;       // offset into bwd_data
+struct BwdPanel {      // one 32-row slice of M_s^T = 32 columns of M_s
+  long long off;       // one copy: offset of the SUPERNODE's first slice in fwd_data (the slices follow: panel_cum);
+                       // with the transposed copy: offset of the slice in bwd_data
   long long rows_off;  // offset into rows (forest row index of each supernode row)
-  int klen;            // number of k steps (even), covering supernode rows [k0, k0+klen) (clipped at h)
-  int k0;              // = row0 (multiple of 32): first supernode row that contributes
+  int klen;            // number of k steps covering supernode rows [k0, k0+klen) (zero rows past h): whole 32-row tiles
+                       // (one copy) or whole k-blocks of 4 (transposed copy)
+  int k0;              // = 32 q: first supernode row that contributes = first column of the slice
   int c0;              // first column of the supernode
   int w, h;
   int pad_;
@@ -71,8 +89,8 @@ struct pcu_bj {
   long long nu = 0;    // rows of the update buffer = sum (h - w)
   double stat[16] = {0};
   // device: factor
-  double* fwd_data = nullptr;
-  double* bwd_data = nullptr;
+  double* fwd_data = nullptr;       // the panels (one copy, both sweeps)
+  double* bwd_data = nullptr;       // optional transposed copy (null: the backward sweep reads fwd_data tile by tile)
   long long fwd_doubles = 0, bwd_doubles = 0;
   pcu::FwdPanel* fwd_panels = nullptr;
   pcu::BwdPanel* bwd_panels = nullptr;

@@ -305,7 +305,9 @@ __global__ void minit_kernel(const SnDev* __restrict__ sns, const double* __rest
 // Panel layout (bj.h): k-blocks of 4 steps; inside a k-block the 128 values are stored in DMMA A-fragment
 // order, element e = lane*4 + rg holding M(row0 + 8*rg + lane/4, 4*kb + lane%4), so that a lane reads its four
 // row-group values of one k-block as 32 contiguous bytes and a warp reads 1 KB contiguous per k-block.
-__global__ void pack_fwd_kernel(const PackTask* __restrict__ tasks, const double* __restrict__ Mbuf, double* __restrict__ out) {
+// ONE copy serves both sweeps (bj.h): the rows below the diagonal block are stored negated, which is what the backward
+// sweep needs (x_s = L_ss^{-T} (y_s - L_bs^T x_anc)); the forward sweep then produces -u_s and the assembly adds it.
+__global__ void pack_kernel(const PackTask* __restrict__ tasks, const double* __restrict__ Mbuf, double* __restrict__ out) {
   const PackTask t = tasks[blockIdx.x];
   const double* M = Mbuf + t.moff;
   double* dst = out + t.dst;
@@ -314,11 +316,12 @@ __global__ void pack_fwd_kernel(const PackTask* __restrict__ tasks, const double
     const int kb = (int)(e / 128), rem = (int)(e % 128), lane = rem / 4, rg = rem % 4;
     const int i = t.row0 + 8 * rg + lane / 4, k = 4 * kb + lane % 4;
     double v = 0.0;
-    if (i < t.h && k < t.w && (i >= t.w || k <= i)) v = M[i + (long long)k * t.h];
+    if (i < t.h && k < t.w && (i >= t.w || k <= i)) { v = M[i + (long long)k * t.h]; if (i >= t.w) v = -v; }
     dst[e] = v;
   }
 }
 
+// The optional transposed copy (bj.h): slice q of M_s^T as one contiguous run of k-blocks, steps = supernode rows 32q..
 __global__ void pack_bwd_kernel(const PackTask* __restrict__ tasks, const double* __restrict__ Mbuf, double* __restrict__ out) {
   const PackTask t = tasks[blockIdx.x];
   const double* M = Mbuf + t.moff;
@@ -530,6 +533,22 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     for (long long i = 0; i < tot; ++i) aent[fill[elev[i]]++] = tmp[i];
   }
   // ---------------------------------------------------------------- solve-side structures
+  // One copy of the panels or two (bj.h)?  The backward sweep is ~10 % faster on the transposed copy (B200, 128^3: apply
+  // 3.48 against 3.60 ms); it is kept when both copies take less than a third of the free device memory, else the
+  // backward sweep reads M tile by tile (half the factor memory: 256^3 then fits 2 GPUs).  PREALPS_BJ_COPIES=1|2 decides.
+  bool tcopy = true;
+  {
+    double est = 0.0;
+    for (int s = 0; s < ns; ++s) {
+      est += (double)panel_cum(sn_w[s], (sn_h[s] + 31) / 32);
+      for (int p = 0; p * 32 < sn_w[s]; ++p) est += 32.0 * ((sn_h[s] - 32 * p + 3) & ~3);
+    }
+    size_t mfree = 0, mtot = 0;
+    PCU_CUDA(cudaMemGetInfo(&mfree, &mtot));
+    tcopy = 8.0 * est <= (double)mfree / 3.0;
+    if (const char* e = getenv("PREALPS_BJ_COPIES")) tcopy = atoi(e) >= 2;
+  }
+  bj->stat[9] = tcopy ? 2.0 : 1.0;
   // panels (sorted by level, long panels first inside a level), work units, gather lists
   std::vector<FwdPanel> fp;
   std::vector<BwdPanel> bp;
@@ -543,14 +562,18 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   bj->bwd_unit_ptr.assign(nlev + 1, 0);
   std::vector<std::vector<PackTask>> pk_f(nlev), pk_b(nlev);
   long long fdoubles = 0, bdoubles = 0;
+  std::vector<long long> sn_doff(ns, 0);  // the panels of a supernode are contiguous, slice after slice (bj.h: panel_cum)
   const int kSplitK = 512;  // without level-adaptive cuts (PREALPS_BJ_NOCHUNK): panels at least this long get a whole CTA
   bj->fwd_tiny0.assign(nlev, 0); bj->fwd_tinyn.assign(nlev, 0);
   bj->bwd_tiny0.assign(nlev, 0); bj->bwd_tinyn.assign(nlev, 0);
   bj->fwd_tinys.assign(nlev, 0); bj->bwd_tinys.assign(nlev, 0);
   const bool use_tiny = getenv("PREALPS_BJ_NOTINY") == nullptr;
   const bool use_chunks = getenv("PREALPS_BJ_NOCHUNK") == nullptr;
-  auto make_units = [&](std::vector<int>& klen_of, int first, int count_all, std::vector<WorkUnit>& units, int* tiny0,
-                        int* tinyn, int* tinys) {
+  // klen_of: steps of a panel rounded to whole k-blocks (the backward kernel walks whole 32-row tiles: its slices are
+  // cut at multiples of 8 k-blocks)
+  auto make_units = [&](std::vector<int>& klen_of, bool tiles, int first, int count_all, std::vector<WorkUnit>& units,
+                        int* tiny0, int* tinyn, int* tinys) {
+    auto cost_kb = [&](int i) { return klen_of[i] / 4; };
     int count = count_all;
     const size_t u_begin = units.size();
     if (use_tiny) while (count > 0 && klen_of[first + count - 1] <= kTinyK) --count;
@@ -561,9 +584,9 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     *tiny0 = first + count;
     *tinyn = count_all - count;
     int cs = count_all;
-    while (cs > count && klen_of[first + cs - 1] <= kTinyS) --cs;
+    while (!tiles && cs > count && klen_of[first + cs - 1] <= kTinyS) --cs;   // a backward slice always lands a whole tile
     *tinys = count_all - cs;
-    // panels [first, first+count) are already sorted by klen descending
+    // panels [first, first+count) are already sorted by cost descending
     int i = 0;
     int slots = 0, ctrs = 0;
     // Work per level is spread over the 148 x 2 resident CTAs x 8 warps: q = k-blocks per warp when every warp slot
@@ -572,7 +595,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     // GPU (strong scaling) the few long panels of a level are spread over the machine instead of being streamed
     // by one warp or one CTA each.
     long long level_kb = 0;
-    for (int j = 0; j < count; ++j) level_kb += klen_of[first + j] / 4;
+    for (int j = 0; j < count; ++j) level_kb += cost_kb(first + j);
     int split_kb = kSplitK / 4, chunk_kb = 1 << 30;
     if (use_chunks) {
       const int q = (int)std::max<long long>(16, (level_kb + kWarpSlots - 1) / kWarpSlots);
@@ -587,9 +610,9 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       chunk_kb = std::max(kChunkMinKB, (per_unit * q + 7) & ~7);
     }
     int nlong = 0;
-    while (nlong < count && klen_of[first + nlong] / 4 >= split_kb) ++nlong;
+    while (nlong < count && cost_kb(first + nlong) >= split_kb) ++nlong;
     while (i < nlong) {
-      const int nkb = klen_of[first + i] / 4;
+      const int nkb = tiles ? ((klen_of[first + i] / 4 + 7) & ~7) : klen_of[first + i] / 4;
       const int nch = (2 * nkb >= 3 * chunk_kb) ? (nkb + chunk_kb - 1) / chunk_kb : 1;
       if (nch <= 1) units.push_back({first + i, 1, 1, 0, nkb, 0, 1, 0, 0, 0});
       else {
@@ -610,8 +633,8 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     if (getenv("PREALPS_BJ_NOLPT") == nullptr) {
       auto cost = [&](const WorkUnit& u) {
         if (u.split == 2) return (u.kb1 - u.kb0 + 7) / 8;
-        if (u.split == 1) return (klen_of[u.first] / 4 + 7) / 8;
-        return klen_of[u.first] / 4;  // the first panel of a group is its longest
+        if (u.split == 1) return (cost_kb(u.first) + 7) / 8;
+        return cost_kb(u.first);  // the first panel of a group is its longest
       };
       std::stable_sort(units.begin() + u_begin, units.end(), [&](const WorkUnit& a, const WorkUnit& b) { return cost(a) > cost(b); });
     }
@@ -621,6 +644,8 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     std::vector<std::pair<int, std::pair<int, int>>> lst;  // (klen, (sn, p))
     for (int q = lev_ptr[l]; q < lev_ptr[l + 1]; ++q) {
       const int s = order[q];
+      sn_doff[s] = fdoubles;
+      fdoubles += panel_cum(sn_w[s], (sn_h[s] + 31) / 32);
       for (int p = 0; p * 32 < sn_h[s]; ++p) {
         int klen = std::min(sn_w[s], 32 * p + 32);
         klen = (klen + 3) & ~3;  // whole k-blocks of 4 (one DMMA step)
@@ -632,43 +657,52 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     std::vector<int> kl;
     for (auto& e : lst) {
       const int s = e.second.first, p = e.second.second;
-      FwdPanel P{fdoubles, uoff[s], e.first, sn_c0[s], 32 * p, sn_w[s], sn_h[s], 0};
-      pk_f[l].push_back({zoff[s], fdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
-      fdoubles += (long long)e.first * 32;
+      const long long poff = sn_doff[s] + panel_cum(sn_w[s], p);
+      FwdPanel P{poff, uoff[s], e.first, sn_c0[s], 32 * p, sn_w[s], sn_h[s], 0};
+      pk_f[l].push_back({zoff[s], poff, sn_h[s], sn_w[s], 32 * p, e.first});
       bj->fwd_lvl_bytes[l] += 8.0 * e.first * 32;
       fp.push_back(P);
       fp_sn.push_back(s);
     }
     kl.resize(fp.size());
     for (size_t i = f0; i < fp.size(); ++i) kl[i] = fp[i].klen;
-    make_units(kl, f0, (int)fp.size() - f0, fu, &bj->fwd_tiny0[l], &bj->fwd_tinyn[l], &bj->fwd_tinys[l]);
+    make_units(kl, false, f0, (int)fp.size() - f0, fu, &bj->fwd_tiny0[l], &bj->fwd_tinyn[l], &bj->fwd_tinys[l]);
     for (int i = bj->fwd_tiny0[l]; i < bj->fwd_tiny0[l] + bj->fwd_tinyn[l]; ++i) bj->fwd_tiny_bytes[l] += 8.0 * kl[i] * 32;
     bj->fwd_unit_ptr[l + 1] = (int)fu.size();
-    // backward
+    // backward: slice q of M_s^T = the 32 columns [32q, 32q + 32) of the SAME panels, walked tile by tile (32 rows of
+    // forward slice p = q, q+1, ...); klen counts rows, whole tiles
     lst.clear();
     for (int q = lev_ptr[l]; q < lev_ptr[l + 1]; ++q) {
       const int s = order[q];
-      for (int p = 0; p * 32 < sn_w[s]; ++p) {
-        int klen = sn_h[s] - 32 * p;
-        klen = (klen + 3) & ~3;  // whole k-blocks of 4 (one DMMA step)
-        lst.push_back({klen, {s, p}});
-      }
+      for (int p = 0; p * 32 < sn_w[s]; ++p) lst.push_back({(sn_h[s] - 32 * p + 3) & ~3, {s, p}});
     }
     std::stable_sort(lst.begin(), lst.end(), [](auto& a, auto& b) { return a.first > b.first; });
     const int b0 = (int)bp.size();
+    std::vector<double> bbytes;
     for (auto& e : lst) {
       const int s = e.second.first, p = e.second.second;
-      BwdPanel P{bdoubles, sn_rp[s], e.first, 32 * p, sn_c0[s], sn_w[s], sn_h[s], 0};
-      pk_b[l].push_back({zoff[s], bdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
-      bdoubles += (long long)e.first * 32;
-      bj->bwd_lvl_bytes[l] += 8.0 * e.first * 32;
-      bp.push_back(P);
+      if (tcopy) {
+        BwdPanel P{bdoubles, sn_rp[s], e.first, 32 * p, sn_c0[s], sn_w[s], sn_h[s], 0};
+        pk_b[l].push_back({zoff[s], bdoubles, sn_h[s], sn_w[s], 32 * p, e.first});
+        bdoubles += (long long)e.first * 32;
+        bbytes.push_back(8.0 * e.first * 32);
+        bp.push_back(P);
+      } else {
+        BwdPanel P{sn_doff[s], sn_rp[s], (e.first + 31) & ~31, 32 * p, sn_c0[s], sn_w[s], sn_h[s], 0};
+        const int nkq = std::min(8, (sn_w[s] + 3) / 4 - 8 * p);
+        bbytes.push_back(8.0 * 128 * nkq * (P.klen / 32));
+        bp.push_back(P);
+      }
+      bj->bwd_lvl_bytes[l] += bbytes.back();
       bp_sn.push_back(s);
     }
     kl.assign(bp.size(), 0);
-    for (size_t i = b0; i < bp.size(); ++i) kl[i] = bp[i].klen;
-    make_units(kl, b0, (int)bp.size() - b0, bu, &bj->bwd_tiny0[l], &bj->bwd_tinyn[l], &bj->bwd_tinys[l]);
-    for (int i = bj->bwd_tiny0[l]; i < bj->bwd_tiny0[l] + bj->bwd_tinyn[l]; ++i) bj->bwd_tiny_bytes[l] += 8.0 * kl[i] * 32;
+    {
+      size_t i = b0;
+      for (auto& e : lst) kl[i++] = e.first;   // the exact length decides who shares a CTA and what is cut
+    }
+    make_units(kl, !tcopy, b0, (int)bp.size() - b0, bu, &bj->bwd_tiny0[l], &bj->bwd_tinyn[l], &bj->bwd_tinys[l]);
+    for (int i = bj->bwd_tiny0[l]; i < bj->bwd_tiny0[l] + bj->bwd_tinyn[l]; ++i) bj->bwd_tiny_bytes[l] += bbytes[i - b0];
     bj->bwd_unit_ptr[l + 1] = (int)bu.size();
   }
   bj->fwd_doubles = fdoubles;
@@ -721,7 +755,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   PCU_CUDA(cudaMemsetAsync(Sbuf, 0, sizeof(double) * std::max<long long>(stot, 1), ctx->stream));
   if (upload(&d_sn, h_sn) || upload(&d_aent, aent) || upload(&d_rel, rel)) return 1;
   PCU_CUDA(cudaMalloc(&bj->fwd_data, sizeof(double) * std::max<long long>(fdoubles, 1)));
-  PCU_CUDA(cudaMalloc(&bj->bwd_data, sizeof(double) * std::max<long long>(bdoubles, 1)));
+  if (tcopy) PCU_CUDA(cudaMalloc(&bj->bwd_data, sizeof(double) * std::max<long long>(bdoubles, 1)));
   if (upload(&bj->fwd_panels, fp) || upload(&bj->bwd_panels, bp) || upload(&bj->fwd_units, fu) ||
       upload(&bj->bwd_units, bu) || upload(&bj->perm, perm) || upload(&bj->rows, rows) ||
       upload(&bj->lvl_cols, lvl_cols) || upload(&bj->gl_ptr, gl_ptr) || upload(&bj->gl_idx, gl_idx))
@@ -824,8 +858,8 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       tilemul_kernel<<<dim3(na_, ytiles(maxh - jb)), kThreads, 0, st>>>(lsn, jb, 0, Zbuf, Mbuf, Dbuf);
       PCU_LAUNCH_CHECK(ctx);
     }
-    // 6. pack M and M^T into panels
-    for (int dir = 0; dir < 2; ++dir) {
+    // 6. pack M into panels, and M^T when the factor keeps the transposed copy
+    for (int dir = 0; dir < (tcopy ? 2 : 1); ++dir) {
       const std::vector<PackTask>& pk = dir == 0 ? pk_f[l] : pk_b[l];
       if (pk.empty()) continue;
       if (pk.size() > pack_cap) {
@@ -835,7 +869,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       }
       PCU_CUDA(cudaStreamSynchronize(st));
       PCU_CUDA(cudaMemcpyAsync(d_pack, pk.data(), sizeof(PackTask) * pk.size(), cudaMemcpyHostToDevice, st));
-      if (dir == 0) pack_fwd_kernel<<<(unsigned)pk.size(), 256, 0, st>>>(d_pack, Mbuf, bj->fwd_data);
+      if (dir == 0) pack_kernel<<<(unsigned)pk.size(), 256, 0, st>>>(d_pack, Mbuf, bj->fwd_data);
       else pack_bwd_kernel<<<(unsigned)pk.size(), 256, 0, st>>>(d_pack, Mbuf, bj->bwd_data);
       PCU_LAUNCH_CHECK(ctx);
     }
@@ -897,11 +931,11 @@ double pcu_bj_bytes(pcu_bj* bj, int t) {
 }
 
 double pcu_bj_stored_bytes(pcu_bj* bj, int t) {
-  // what the kernels have to move: both copies of the stored panels (explicit zeros of the relaxed supernodes and the
-  // padding of the 32-row panels included), the block vectors (read B, write/read Wk and Y once each, write X) and
+  // what the kernels have to move: the stored panels once per sweep (explicit zeros of the relaxed supernodes and the
+  // padding of the 32-row panels included; with one copy in memory both sweeps read the same panels), the block vectors (read B, write/read Wk and Y once each, write X) and
   // the update rows (written by the forward sweep, gathered by the assembly)
   const double vec = (double)bj->n * t * 8.0;
-  return 8.0 * ((double)bj->fwd_doubles + (double)bj->bwd_doubles) + 6.0 * vec +
+  return 8.0 * ((double)bj->fwd_doubles + (bj->bwd_data ? (double)bj->bwd_doubles : (double)bj->fwd_doubles)) + 6.0 * vec +
          2.0 * (double)bj->nu * t * 8.0 + (double)bj->nu * 8.0;
 }
 

@@ -6,7 +6,7 @@
 // With the factor stored as M_s = [L_ss^{-1}; L_bs L_ss^{-1}] (bj.h) every level is
 //   forward : assemble  b_s = B[perm] - sum(update rows of the descendants)   (gather, fixed order)
 //             panels    [y_s ; u_s] = M_s b_s                                  (streaming)
-//   backward: panels    x_s = M_s^T [y_s ; -x_ancestors]                       (streaming)
+//   backward: panels    x_s = M_s^T [y_s ; -x_ancestors]                       (streaming, the SAME panels, bj.h)
 // The streaming kernel is HBM-bound: a warp reads a 32-row k-major panel with 512-byte
 // coalesced loads (each lane a double2 = two rows of one k), the T-wide input row of step
 // k is identical for the 16 lanes of a half-warp (broadcast load), every lane keeps
@@ -48,7 +48,8 @@ inline void pdl_launch_dependents() {}
 // length is what the launch costs), NB = 8 (fewer registers, more resident warps) where the lists are short or empty.
 // Slots past the end of a list point at row `pad` of U, which is zero and never written: the loads of a batch carry no
 // predicate, and with the minimum-CTAs launch bound ptxas issues them back to back instead of sinking each next to its
-// subtraction (x - 0.0 == x: the padding does not change a bit).
+// addition (the padding adds 0.0).  The update rows arrive NEGATED (the rows of M_s below the diagonal block are stored
+// negated for the backward sweep, bj.h), so the assembly adds them: b_s = B - sum(u) as before, bit for bit.
 template <int T, int NB>
 __global__ void __launch_bounds__(kThreads, NB == 16 ? 2 : 4) assemble_kernel(const int* __restrict__ cols, int ncols,
                                                                               const double* __restrict__ B, int ldb, int t,
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, NB == 16 ? 2 : 4) assemble_kernel(co
 #pragma unroll
       for (int j = 0; j < NB; ++j) idx[j] = (g + NB + j < g1) ? __ldg(gl_idx + g + NB + j) : pad;  // next batch
 #pragma unroll
-      for (int j = 0; j < NB; ++j) { a0 -= v[j].x; a1 -= v[j].y; }
+      for (int j = 0; j < NB; ++j) { a0 += v[j].x; a1 += v[j].y; }
     }
     double* dst = Wk + (size_t)c * T + c0;
     if (CPL == 2) *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
@@ -165,8 +166,11 @@ inline void cp_async_wait() {}
 #endif
 
 // rows of the input block staged per tile and per warp (4 KB per buffer at any T)
-template <int T>
-struct Tile { static constexpr int KT = (T <= 8) ? 64 : (512 / T); };  // k steps per tile, even, KT*T*8 = 4 KB for T >= 8
+template <int T, bool FWD>
+struct Tile {  // k steps per tile, even, KT*T*8 = 4 KB for T >= 8; the backward sweep consumes whole 32-row tiles of M
+  static constexpr int KT0 = (T <= 8) ? 64 : (512 / T);
+  static constexpr int KT = (!FWD && KT0 < 32) ? 32 : KT0;
+};
 
 
 #ifndef PCU_EMUL
@@ -190,6 +194,16 @@ inline void dmma884(double& d0, double& d1, double a, double b) {
 }
 #define PCU_DYN_SMEM(name) double* name = static_cast<double*>(emul_dyn_smem())
 #endif
+
+// Backward sweep: the A fragments of M_s^T straight out of the forward panels.  In a k-block (32 rows x 4 columns) the
+// 32 bytes of "slot" s hold M(8*rg + s/4, 4*kb + s%4), rg = 0..3.  For the 32 rows x 8 columns of two consecutive k-blocks
+// (a unit) lane l needs, as the A fragment of step group ib = 0..7, M(4*ib + l%4, 8-column index l/4): k-block l/16, slot
+// 16*(ib%2) + 4*(l%4) + (l/4)%4, register ib/2.  So a lane reads the slots 4*(l%4) + (l/4)%4 (ib even) and 16 more (ib
+// odd) of k-block l/16 -- two 32-byte loads per unit like the forward sweep, the warp covering 2 x 512 contiguous bytes
+// per load: the transposition is in the addressing, there is nothing to exchange between lanes.
+__device__ __forceinline__ int bwd_lane_offset(int lane) {   // doubles, relative to the unit's first k-block
+  return (lane >> 4) * 128 + (4 * (lane & 3) + ((lane >> 2) & 3)) * 4;
+}
 
 // lane owns, for every row group rg and column block nb: row row0 + 8*rg + lane/4, columns 8*nb + 2*(lane%4) + {0,1}
 template <int T, bool FWD>
@@ -237,10 +251,13 @@ __device__ __forceinline__ void store_outputs(const double (&acc)[4][(T + 7) / 8
 //       the ring: 3 CTAs/SM = 24 warps x 4 KB in flight.
 // History (128^3, t=8, whole apply): plain FMA loop 2.1 TB/s (long-scoreboard bound), + register ring 2.6,
 // + cp.async tiles 3.5, DMMA + fragment-order panels: see profiles/.
-template <int T, bool FWD, int D, bool NOALLOC, int OCC>
-__global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(SweepArgs a) {
+// TCOPY (backward only): the factor also holds the transposed panels (bj.h), the backward sweep streams them exactly like
+// the forward sweep streams M; without them it reads M tile by tile.
+template <int T, bool FWD, int D, bool NOALLOC, int OCC, bool TCOPY>
+__global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD && !TCOPY) ? 1 : 2)) sweep_kernel(SweepArgs a) {
+  constexpr bool STREAM = FWD || TCOPY;   // the panel is one contiguous run of k-blocks
   constexpr int NB = (T + 7) / 8;       // 8-column blocks of the output
-  constexpr int KT = Tile<T>::KT;       // k steps per input tile
+  constexpr int KT = Tile<T, STREAM>::KT;  // k steps per input tile
   constexpr int KB = KT / 4;            // k-blocks per tile
   constexpr int TILE = KT * T;          // doubles per tile buffer
   static_assert(KB % D == 0, "ring depth must divide the k-blocks of a tile");
@@ -276,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
   for (int rg = 0; rg < 4; ++rg)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
-  const double* base = a.data + off + lane * 4;
+  const double* base = a.data + off + lane * 4;   // forward: the panel; backward: the supernode's first slice
   const int* rows = a.rows + rows_off;
 
   // copy the input rows of steps [4*tq, 4*tq + KT) into buf (steps past the panel are clamped: their
@@ -308,50 +325,117 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
     cp_async_commit();
   };
 
-  double2 ring0[D], ring1[D];
-  auto issue = [&](int kb, double2& m0, double2& m1) {
-    if (kb < q1) {
-      const double* p = base + (size_t)kb * 128;
-      if (NOALLOC) ld_stream4(p, m0, m1);
-      else { m0 = __ldg(reinterpret_cast<const double2*>(p)); m1 = __ldg(reinterpret_cast<const double2*>(p + 2)); }
-    } else {
-      m0 = make_double2(0.0, 0.0);
-      m1 = m0;
+  if constexpr (STREAM) {
+    double2 ring0[D], ring1[D];
+    auto issue = [&](int kb, double2& m0, double2& m1) {
+      if (kb < q1) {
+        const double* p = base + (size_t)kb * 128;
+        if (NOALLOC) ld_stream4(p, m0, m1);
+        else { m0 = __ldg(reinterpret_cast<const double2*>(p)); m1 = __ldg(reinterpret_cast<const double2*>(p + 2)); }
+      } else {
+        m0 = make_double2(0.0, 0.0);
+        m1 = m0;
+      }
+    };
+    // panel data does not depend on the previous kernel: in flight before the wait
+    if (q0 < q1) {
+#pragma unroll
+      for (int u2 = 0; u2 < D; ++u2) issue(q0 + u2, ring0[u2], ring1[u2]);
     }
-  };
-  // panel data does not depend on the previous kernel: in flight before the wait
-  if (q0 < q1) {
-#pragma unroll
-    for (int u2 = 0; u2 < D; ++u2) issue(q0 + u2, ring0[u2], ring1[u2]);
-  }
-  pdl_wait();
-  pdl_launch_dependents();
-  if (q0 < q1) {
-    stage(q0, tile0);
-    int tix = 0;
-    for (int tq = q0; tq < q1; tq += KB, ++tix) {
-      const double* cur = tile0 + (size_t)(tix & 1) * TILE;
-      if (tq + KB < q1) { stage(tq + KB, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
-      __syncwarp();
+    pdl_wait();
+    pdl_launch_dependents();
+    if (q0 < q1) {
+      stage(q0, tile0);
+      int tix = 0;
+      for (int tq = q0; tq < q1; tq += KB, ++tix) {
+        const double* cur = tile0 + (size_t)(tix & 1) * TILE;
+        if (tq + KB < q1) { stage(tq + KB, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
 #pragma unroll 1
-      for (int kq = 0; kq < KB; kq += D) {
+        for (int kq = 0; kq < KB; kq += D) {
 #pragma unroll
-        for (int u2 = 0; u2 < D; ++u2) {
-          const double2 m0 = ring0[u2], m1 = ring1[u2];
-          issue(tq + kq + u2 + D, ring0[u2], ring1[u2]);
-          const double* brow = cur + (size_t)(4 * (kq + u2) + lk) * T;
+          for (int u2 = 0; u2 < D; ++u2) {
+            const double2 m0 = ring0[u2], m1 = ring1[u2];
+            issue(tq + kq + u2 + D, ring0[u2], ring1[u2]);
+            const double* brow = cur + (size_t)(4 * (kq + u2) + lk) * T;
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
-            dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
-            dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
-            dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
-            dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+            for (int nb = 0; nb < NB; ++nb) {
+              const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
+              dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
+              dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
+              dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
+              dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+            }
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
+    }
+  } else {
+    // Backward: the slice is the 32 columns [row0, row0 + 32) of the supernode's forward panels.  Tile by tile (32 rows
+    // of forward slice p = row0/32 + tile), the k-blocks [8*qcol, 8*qcol + nkq) of that slice are read in units of two
+    // (2 KB; the ring holds two units = the 4 KB in flight per warp of the forward sweep) in the lane order of
+    // bwd_lane_offset: unit jg feeds the output rows [8*jg, 8*jg + 8) with the tile's 32 input rows (8 DMMA steps).
+    static_assert(KB % 8 == 0, "the backward sweep consumes whole 32-row tiles");
+    const int W4 = (w + 3) >> 2;
+    const int qcol = row0 >> 5;
+    const int nkq = min(8, W4 - 8 * qcol);
+    const int tl1 = q1 >> 3;
+    const int khalf = lane >> 4;   // which k-block of a unit this lane reads
+    int pcur = qcol + (q0 >> 3);
+    const double* cur_base = a.data + off + panel_cum(w, pcur) + (long long)qcol * 1024 + bwd_lane_offset(lane);
+    const double* nxt_base = cur_base + 128ll * min(W4, 8 * pcur + 8);
+    double2 ue0[2], ue1[2], uo0[2], uo1[2];   // per ring slot: even steps (ib = 0, 2, 4, 6), odd steps
+    auto issue_unit = [&](const double* tb, int jg, bool valid, double2& e0, double2& e1, double2& o0, double2& o1) {
+      if (valid && 2 * jg + khalf < nkq) {
+        ld_stream4(tb + (size_t)(2 * jg) * 128, e0, e1);
+        ld_stream4(tb + (size_t)(2 * jg) * 128 + 64, o0, o1);
+      } else {
+        e0 = make_double2(0.0, 0.0); e1 = e0; o0 = e0; o1 = e0;
+      }
+    };
+    issue_unit(cur_base, 0, q0 < q1, ue0[0], ue1[0], uo0[0], uo1[0]);
+    issue_unit(cur_base, 1, q0 < q1, ue0[1], ue1[1], uo0[1], uo1[1]);
+    pdl_wait();
+    pdl_launch_dependents();
+    if (q0 < q1) {
+      stage(q0, tile0);
+      int tix = 0;
+      for (int tq = q0; tq < q1; tq += KB, ++tix) {
+        const double* cur = tile0 + (size_t)(tix & 1) * TILE;
+        if (tq + KB < q1) { stage(tq + KB, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int mt = 0; mt < KB / 8; ++mt) {
+          const int ti = (tq >> 3) + mt;   // tile of the slice
+          if (ti >= tl1) break;
+          const bool more = ti + 1 < tl1;
+#pragma unroll
+          for (int jg = 0; jg < 4; ++jg) {
+            const bool live = 2 * jg < nkq;
+            const double av[8] = {ue0[jg & 1].x, uo0[jg & 1].x, ue0[jg & 1].y, uo0[jg & 1].y,
+                                  ue1[jg & 1].x, uo1[jg & 1].x, ue1[jg & 1].y, uo1[jg & 1].y};
+            if (jg < 2) issue_unit(cur_base, jg + 2, true, ue0[jg & 1], ue1[jg & 1], uo0[jg & 1], uo1[jg & 1]);
+            else issue_unit(nxt_base, jg - 2, more, ue0[jg & 1], ue1[jg & 1], uo0[jg & 1], uo1[jg & 1]);
+            if (live) {
+              const double* brow = cur + (size_t)(32 * mt + lk) * T;
+#pragma unroll
+              for (int ib = 0; ib < 8; ++ib)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                  const double bf = (8 * nb + lr < T) ? brow[(size_t)(4 * ib) * T + 8 * nb + lr] : 0.0;
+                  dmma884(acc[jg][nb][0], acc[jg][nb][1], av[ib], bf);
+                }
+            }
+          }
+          ++pcur;
+          cur_base = nxt_base;
+          nxt_base += 128ll * min(W4, 8 * pcur + 8);
+        }
+        __syncwarp();
+      }
     }
   }
   // lane owns, for every row group rg and column block nb: row 8*rg + lane/4, columns 8*nb + 2*(lane%4) + {0,1}
@@ -410,8 +494,9 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : 2) sweep_kernel(Swe
 // Tiny panels (klen <= kTinyK steps, the leaves of the elimination forest: most of the supernodes but ~10 % of
 // the data): one warp per panel, the WHOLE panel (<= 16 KB) and its input rows are copied to shared memory with
 // cp.async in one go, so 20 KB per warp are in flight and there is no per-tile latency chain; 4 warps per CTA.
-template <int T, bool FWD, int KMAX, int WARPS>
+template <int T, bool FWD, int KMAX, int WARPS, bool TCOPY>
 __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int first, int count) {
+  constexpr bool STREAM = FWD || TCOPY;
   constexpr int NB = (T + 7) / 8;
   constexpr int MB = KMAX * 32;         // doubles of panel data per warp
   constexpr int BB = KMAX * T;          // doubles of input rows per warp
@@ -432,13 +517,32 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
     const BwdPanel p = reinterpret_cast<const BwdPanel*>(a.panels)[first + q];
     off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
   }
-  const int nkb = klen >> 2;
-  const double* base = a.data + off + lane * 4;
+  // forward: the whole panel; backward: the k-blocks of the slice's 32 columns in the supernode's LAST forward slice
+  // (a one-tile backward slice: row0 = 32 * (slices - 1))
+  const int qcol = row0 >> 5;
+  const int nkb = STREAM ? (klen >> 2) : min(8, ((w + 3) >> 2) - 8 * qcol);
   const int* rows = a.rows + rows_off;
   const unsigned long long pol = l2_evict_first_policy();
-  for (int kb = 0; kb < nkb; ++kb) {
-    cp_async16_stream(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128, pol);
-    cp_async16_stream(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2, pol);
+  if constexpr (STREAM) {
+    const double* base = a.data + off + lane * 4;
+    for (int kb = 0; kb < nkb; ++kb) {
+      cp_async16_stream(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128, pol);
+      cp_async16_stream(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2, pol);
+    }
+  } else {
+    // lands in the lane order of the backward A fragments (bwd_lane_offset): unit jg, even steps then odd steps
+    const double* base = a.data + off + panel_cum(w, qcol) + (long long)qcol * 1024 + bwd_lane_offset(lane);
+    for (int jg = 0; 2 * jg < nkb; ++jg)
+      for (int par = 0; par < 2; ++par) {
+        double* dst = mbuf + ((2 * jg + par) * 32 + lane) * 4;
+        if (2 * jg + (lane >> 4) < nkb) {
+          const double* src = base + (size_t)(2 * jg) * 128 + 64 * par;
+          cp_async16_stream(dst, src, pol);
+          cp_async16_stream(dst + 2, src + 2, pol);
+        } else {
+          dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
+        }
+      }
   }
   pdl_wait();   // the panel itself is static; the input rows come from the previous kernel
   pdl_launch_dependents();
@@ -471,18 +575,38 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
     for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
   cp_async_wait<0>();
   __syncwarp();
+  if constexpr (STREAM) {
 #pragma unroll 2
-  for (int kb = 0; kb < nkb; ++kb) {
-    const double2 m0 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4);
-    const double2 m1 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4 + 2);
-    const double* brow = bbuf + (size_t)(4 * kb + lk) * T;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const double2 m0 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4);
+      const double2 m1 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4 + 2);
+      const double* brow = bbuf + (size_t)(4 * kb + lk) * T;
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
-      dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
-      dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
-      dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
-      dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+      for (int nb = 0; nb < NB; ++nb) {
+        const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
+        dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
+        dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
+        dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
+        dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int jg = 0; jg < 4; ++jg) {
+      if (2 * jg >= nkb) break;
+      const double* me = mbuf + ((2 * jg) * 32 + lane) * 4;
+      const double2 e0 = *reinterpret_cast<const double2*>(me), e1 = *reinterpret_cast<const double2*>(me + 2);
+      const double2 o0 = *reinterpret_cast<const double2*>(me + 128), o1 = *reinterpret_cast<const double2*>(me + 130);
+      const double av[8] = {e0.x, o0.x, e0.y, o0.y, e1.x, o1.x, e1.y, o1.y};
+#pragma unroll
+      for (int ib = 0; ib < 8; ++ib) {
+        const double* brow = bbuf + (size_t)(4 * ib + lk) * T;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
+          dmma884(acc[jg][nb][0], acc[jg][nb][1], av[ib], bf);
+        }
+      }
     }
   }
   store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
@@ -531,42 +655,48 @@ void launch_chain(void (*kernel)(KArgs...), int grid, int block, size_t smem, cu
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-template <int T, bool FWD, int D, bool NOALLOC, int OCC>
+template <int T, bool FWD, int D, bool NOALLOC, int OCC, bool TCOPY>
 void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
-  constexpr int bytes = (32 * T + kWarps * 2 * Tile<T>::KT * T) * (int)sizeof(double);
+  constexpr int bytes = (32 * T + kWarps * 2 * Tile<T, FWD || TCOPY>::KT * T) * (int)sizeof(double);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_kernel<T, FWD, D, NOALLOC, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(sweep_kernel<T, FWD, D, NOALLOC, OCC, TCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     configured = true;
   }
-  launch_chain(sweep_kernel<T, FWD, D, NOALLOC, OCC>, nu, kThreads, bytes, st, a);
+  launch_chain(sweep_kernel<T, FWD, D, NOALLOC, OCC, TCOPY>, nu, kThreads, bytes, st, a);
 }
 
-template <int T, bool FWD, int KMAX, int WARPS>
+template <int T, bool FWD, int KMAX, int WARPS, bool TCOPY>
 void launch_tiny_one(int first, int count, cudaStream_t st, const SweepArgs& a) {
   constexpr int bytes = WARPS * (KMAX * 32 + KMAX * T) * (int)sizeof(double);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(sweep_tiny_kernel<T, FWD, KMAX, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(sweep_tiny_kernel<T, FWD, KMAX, WARPS, TCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     configured = true;
   }
-  launch_chain(sweep_tiny_kernel<T, FWD, KMAX, WARPS>, (count + WARPS - 1) / WARPS, WARPS * 32, bytes, st, a, first, count);
+  launch_chain(sweep_tiny_kernel<T, FWD, KMAX, WARPS, TCOPY>, (count + WARPS - 1) / WARPS, WARPS * 32, bytes, st, a, first, count);
 }
 
 // panels [first, first + count) are sorted by length, the last `nshort` ones have klen <= kTinyS: each class gets a
 // landing buffer of its own size (more resident warps for the shorter panels)
 template <int T, bool FWD>
-void launch_tiny(int first, int count, int nshort, cudaStream_t st, const SweepArgs& a) {
+void launch_tiny(int first, int count, int nshort, cudaStream_t st, const SweepArgs& a, bool tcopy) {
   const int nlong = count - nshort;
-  if (nlong > 0) launch_tiny_one<T, FWD, kTinyK, 4>(first, nlong, st, a);
-  if (nshort > 0) launch_tiny_one<T, FWD, kTinyS, 8>(first + nlong, nshort, st, a);
+  if (FWD || tcopy) {
+    if (nlong > 0) launch_tiny_one<T, FWD, kTinyK, 4, !FWD>(first, nlong, st, a);
+    if (nshort > 0) launch_tiny_one<T, FWD, kTinyS, 8, !FWD>(first + nlong, nshort, st, a);
+  } else {
+    launch_tiny_one<T, false, kTinyK, 4, false>(first, count, st, a);   // a tile-wise backward slice always lands a whole tile
+  }
 }
 
 template <int T, bool FWD>
-void launch_sweep(int nu, cudaStream_t st, const SweepArgs& a) {
+void launch_sweep(int nu, cudaStream_t st, const SweepArgs& a, bool tcopy) {
   // ring of 4 k-blocks per warp, streaming (no L1 allocation) panel loads, 2 CTAs per SM: the best of the
   // combinations measured on B200 (deeper rings and 3 CTAs/SM spill; allocating loads are 2 % slower)
-  launch_one<T, FWD, 4, true, 2>(nu, st, a);
+  if (FWD) launch_one<T, FWD, 4, true, 2, false>(nu, st, a);
+  else if (tcopy) launch_one<T, false, 4, true, 2, true>(nu, st, a);
+  else launch_one<T, false, 4, true, 2, false>(nu, st, a);
 }
 
 // PREALPS_BJ_PROFILE=1: per-launch CUDA-event timings of one apply, printed to stderr
@@ -630,14 +760,14 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       a.units = bj->fwd_units + bj->fwd_unit_ptr[l];
       a.panels = bj->fwd_panels;
       a.data = bj->fwd_data;
-      launch_sweep<T, true>(nu, st, a);
+      launch_sweep<T, true>(nu, st, a, false);
       PCU_LAUNCH_CHECK(c);
     }
     if (bj->fwd_tinyn[l] > 0) {
       prof.mark("fwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->fwd_tinyn[l]) + "/" + std::to_string(bj->fwd_tinys[l]), bj->fwd_tiny_bytes[l]);
       a.panels = bj->fwd_panels;
       a.data = bj->fwd_data;
-      launch_tiny<T, true>(bj->fwd_tiny0[l], bj->fwd_tinyn[l], bj->fwd_tinys[l], st, a);
+      launch_tiny<T, true>(bj->fwd_tiny0[l], bj->fwd_tinyn[l], bj->fwd_tinys[l], st, a, false);
       c->launches++;
       PCU_LAUNCH_CHECK(c);
     }
@@ -648,15 +778,15 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
       prof.mark("bwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->bwd_lvl_bytes[l] - bj->bwd_tiny_bytes[l]);
       a.units = bj->bwd_units + bj->bwd_unit_ptr[l];
       a.panels = bj->bwd_panels;
-      a.data = bj->bwd_data;
-      launch_sweep<T, false>(nu, st, a);
+      a.data = bj->bwd_data ? bj->bwd_data : bj->fwd_data;
+      launch_sweep<T, false>(nu, st, a, bj->bwd_data != nullptr);
       PCU_LAUNCH_CHECK(c);
     }
     if (bj->bwd_tinyn[l] > 0) {
       prof.mark("bwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->bwd_tinyn[l]) + "/" + std::to_string(bj->bwd_tinys[l]), bj->bwd_tiny_bytes[l]);
       a.panels = bj->bwd_panels;
-      a.data = bj->bwd_data;
-      launch_tiny<T, false>(bj->bwd_tiny0[l], bj->bwd_tinyn[l], bj->bwd_tinys[l], st, a);
+      a.data = bj->bwd_data ? bj->bwd_data : bj->fwd_data;
+      launch_tiny<T, false>(bj->bwd_tiny0[l], bj->bwd_tinyn[l], bj->bwd_tinys[l], st, a, bj->bwd_data != nullptr);
       c->launches++;
       PCU_LAUNCH_CHECK(c);
     }

@@ -141,6 +141,7 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
   return cudaSuccess;
 }
 inline cudaError_t cudaFree(void* p) { if (p) emul_unregister(p); std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)64 << 30; return cudaSuccess; }
 template <class T> inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
 inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { *p = static_cast<T*>(std::malloc(bytes ? bytes : 8)); return *p ? cudaSuccess : 2; }

@@ -200,9 +200,12 @@ def test_split_sum_fro(dev):
 
 @pytest.mark.parametrize("gen,N,nblk", [("poisson7", 8, 1), ("poisson7", 12, 3), ("stencil27", 9, 2), ("poisson7", 20, 2)])
 @pytest.mark.parametrize("t", [1, 4, 8, 16])
-def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t):
-    """pcu_bj_create + pcu_bj_apply against a direct sparse solve of every diagonal block"""
+@pytest.mark.parametrize("copies", [2, 1])
+def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t, copies, monkeypatch):
+    """pcu_bj_create + pcu_bj_apply against a direct sparse solve of every diagonal block; with the transposed copy of the
+    panels (copies = 2) and with the backward sweep reading the forward panels tile by tile (copies = 1)"""
     import scipy.sparse.linalg as spla
+    monkeypatch.setenv("PREALPS_BJ_COPIES", str(copies))
     A = getattr(gen_matrices, gen)(N).tocsr()
     n = A.shape[0]
     cuts = np.linspace(0, n, nblk + 1).astype(np.int32)
@@ -229,13 +232,16 @@ def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t):
     assert cu.pcu_bj_apply(bj, dB, ld, dB, ld, t) == 0
     assert np.array_equal(dev.down(dB, (n, ld)), X)
     assert cu.pcu_bj_stat(bj, 0) > 0 and cu.pcu_bj_stat(bj, 1) >= cu.pcu_bj_stat(bj, 0)
+    assert cu.pcu_bj_stat(bj, 9) == copies
     dev.free(dB, dX)
     cu.pcu_bj_destroy(bj)
 
 
-def test_block_jacobi_long_panels_cut_across_ctas(dev):
+@pytest.mark.parametrize("copies", [2, 1])
+def test_block_jacobi_long_panels_cut_across_ctas(dev, copies, monkeypatch):
     """a block large enough for separators beyond 1024 columns: exercises the inter-CTA split of long panels"""
     import scipy.sparse.linalg as spla
+    monkeypatch.setenv("PREALPS_BJ_COPIES", str(copies))
     A = gen_matrices.poisson7(36).tocsr()
     n = A.shape[0]
     U = sp.triu(A, format="csr"); U.sort_indices()
@@ -246,7 +252,7 @@ def test_block_jacobi_long_panels_cut_across_ctas(dev):
     assert cu.pcu_bj_create(dev.ctx, 1, capi.ip(np.array([0, n], np.int32)), rp, ci, vv, C.byref(bj)) == 0, cu.pcu_last_error()
     rng = np.random.default_rng(3)
     lu = spla.splu(A.tocsc())
-    for t in (8, 4, 16):
+    for t in (8, 4, 16, 32):
         B = rng.standard_normal((n, t))
         dB, dX = dev.up(B), dev.zeros(n * t)
         for rep in range(2):  # the second apply re-uses the arrival counters
