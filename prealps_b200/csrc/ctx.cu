@@ -253,10 +253,21 @@ int pcu_ctx_init_nccl(pcu_ctx* c, int nranks, int rank, const void* id128) {
   PCU_NCCL(g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank));
   // NCCL sets its channels up on the first collective (8 ranks: ~8 s, which round 1 had mistaken for eight METIS runs
   // competing for the host): pay for it here, once, where it can be told apart from the operator build
+  // ... and so are the broadcast ring (the partition is broadcast from rank 0) and the point-to-point connections (halo
+  // plan and halo exchange): one grouped send/recv with every peer connects them all at once instead of one by one
+  // inside the first operator build
   double* d = nullptr;
-  PCU_CUDA(cudaMalloc(&d, sizeof(double)));
-  PCU_CUDA(cudaMemsetAsync(d, 0, sizeof(double), c->stream));
+  PCU_CUDA(cudaMalloc(&d, sizeof(double) * (size_t)(2 * nranks + 2)));
+  PCU_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)(2 * nranks + 2), c->stream));
   PCU_NCCL(g_nccl.AllReduce(d, d, 1, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream));
+  PCU_NCCL(g_nccl.Broadcast(d, d, 1, kNcclFloat64, 0, c->nccl_comm, c->stream));
+  if (nccl_group_start(c)) return 1;
+  for (int q = 0; q < nranks; ++q) {
+    if (q == rank) continue;
+    PCU_NCCL(g_nccl.Send(d + 2 + q, 1, kNcclFloat64, q, c->nccl_comm, c->stream));
+    PCU_NCCL(g_nccl.Recv(d + 2 + nranks + q, 1, kNcclFloat64, q, c->nccl_comm, c->stream));
+  }
+  if (nccl_group_end(c)) return 1;
   PCU_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d);
   return 0;

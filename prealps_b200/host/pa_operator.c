@@ -455,10 +455,16 @@ int preAlps_b200_OperatorBuildFile(const char* mtx, int S, int s_lo, int s_hi) {
 
 int preAlps_b200_OperatorBuildStencil(int kind, int N, int S, int s_lo, int s_hi) {
   set_single_or_nccl(S, s_lo, s_hi);
+  const int timing = getenv("PREALPS_B200_TIMING") != NULL;
+  double t0 = pa_wtime();
   CPLM_Mat_CSR_t G = CPLM_MatCSRNULL();
   pa_stencil_csr(kind, N, &G);
+  if (timing) fprintf(stderr, "[prealps_b200] setup: %-28s %.3f s\n", "stencil generation", pa_wtime() - t0);
   partition_global(&G, S, s_lo, s_hi, 1, NULL);
-  return finish_build();
+  t0 = pa_wtime();
+  const int rc = finish_build();
+  if (timing) fprintf(stderr, "[prealps_b200] setup: %-28s %.3f s\n", "halo plan + device upload", pa_wtime() - t0);
+  return rc;
 }
 
 /* ------------------------------------------------------------------ getters (ref: operator.c:353-393) */

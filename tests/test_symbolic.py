@@ -83,4 +83,11 @@ def test_relaxation_bounds_fill():
     U = sp.triu(A, format="csr")
     U.sort_indices()
     *_, st = analyze(U, 1)
-    assert st[1] <= 2.0 * st[0]
+    # leaf subtrees of up to 48 columns become one dense supernode (the B200 sweep's default): on a 10^3 block, where most
+    # of the factor sits in such leaves, that is ~2.05x the exact non-zeros, 1.40x at 24^3, 1.13x at 64^3 (tools/bj_layout_stats.py)
+    assert st[1] <= 2.5 * st[0]
+    A = gen_matrices.poisson7(24).tocsr()
+    U = sp.triu(A, format="csr")
+    U.sort_indices()
+    *_, st = analyze(U, 1)
+    assert st[1] <= 1.5 * st[0]
