@@ -114,6 +114,8 @@ struct SweepArgs {
   const void* panels;
   const double* data;
   const double* Wk;     // fwd input
+  const double* Bsrc;   // fwd, leaves only: read the caller's block directly (row perm[c], ld ldb) instead of Wk -- the
+  int ldb;              // columns of a leaf gather nothing, their assembly would be a plain permuted copy
   double* Y;            // fwd output (own columns) / bwd input (own columns)
   double* U;            // fwd output (update rows)
   double* Xp;           // bwd output + input (ancestors), forest order
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
         const int r = q / CPR, part = q % CPR;
         const int k = min(4 * tq + r, klen - 1);
         const double* src;
-        if (FWD) src = a.Wk + (size_t)(c0 + k) * T;
+        if (FWD) src = a.Bsrc ? a.Bsrc + (size_t)__ldg(a.perm + c0 + k) * a.ldb : a.Wk + (size_t)(c0 + k) * T;
         else {
           const int i = min(row0 + k, h - 1);
           src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
       } else if (q < KT) {
         const int k = min(4 * tq + q, klen - 1);
         const double* src;
-        if (FWD) src = a.Wk + (size_t)(c0 + k);
+        if (FWD) src = a.Bsrc ? a.Bsrc + (size_t)__ldg(a.perm + c0 + k) * a.ldb : a.Wk + (size_t)(c0 + k);
         else { const int i = min(row0 + k, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
         buf[q] = *src;
       }
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
     for (int qq = lane; qq < chunks; qq += 32) {
       const int r = qq / CPR, part = qq % CPR;
       const double* src;
-      if (FWD) src = a.Wk + (size_t)(c0 + r) * T;
+      if (FWD) src = a.Bsrc ? a.Bsrc + (size_t)__ldg(a.perm + c0 + r) * a.ldb : a.Wk + (size_t)(c0 + r) * T;
       else {
         const int i = min(row0 + r, h - 1);
         src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
   } else {
     for (int r = lane; r < klen; r += 32) {
       const double* src;
-      if (FWD) src = a.Wk + (size_t)(c0 + r);
+      if (FWD) src = a.Bsrc ? a.Bsrc + (size_t)__ldg(a.perm + c0 + r) * a.ldb : a.Wk + (size_t)(c0 + r);
       else { const int i = min(row0 + r, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
       bbuf[r] = *src;
     }
@@ -741,9 +743,15 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   a.Wk = bj->Wk; a.Y = bj->Y; a.U = bj->U; a.Xp = bj->Xp; a.rows = bj->rows; a.perm = bj->perm;
   a.Out = X; a.ldo = ldx; a.t = t;
   a.scratch = bj->scratch; a.counters = bj->counters;
+  // level 0 = the leaves: nothing to gather, so the forward panels read B[perm] themselves when the caller's rows can
+  // be copied T wide in 16-byte pieces (t == T, even leading dimension, aligned base)
+  static const bool leaf_direct_on = getenv("PREALPS_BJ_NO_LEAF_DIRECT") == nullptr;
+  const bool leaf_direct = leaf_direct_on && t == T && (T == 1 || (ldb % 2 == 0 && (reinterpret_cast<size_t>(B) & 15) == 0));
   for (int l = 0; l < bj->nlevels; ++l) {
     const int ncols = bj->lvl_col_ptr[l + 1] - bj->lvl_col_ptr[l];
-    if (ncols > 0) {
+    a.Bsrc = (l == 0 && leaf_direct) ? B : nullptr;
+    a.ldb = ldb;
+    if (ncols > 0 && a.Bsrc == nullptr) {
       prof.mark("asm L" + std::to_string(l) + " cols=" + std::to_string(ncols), 3.0 * ncols * T * 8);
       const int grid = stream_grid(c, (long long)ncols * G, kThreads, 8);
       if (bj->lvl_long_lists[l])
