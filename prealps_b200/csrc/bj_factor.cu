@@ -16,6 +16,7 @@
 // children of one parent are extend-added in separate rounds => bit-reproducible.
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <numeric>
 #include <thread>
 
@@ -460,11 +461,61 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   // update-buffer slots, global S offsets, level-local Z/M/D offsets
   std::vector<long long> uoff(ns), soff(ns), zoff(ns), doff(ns);
   long long nu = 0, stot = 0, zmax = 0, dmax = 0;
-  for (int s = 0; s < ns; ++s) {
-    uoff[s] = nu; nu += sn_h[s] - sn_w[s];
-    soff[s] = stot; stot += (long long)(sn_h[s] - sn_w[s]) * (sn_h[s] - sn_w[s]);
-  }
+  for (int s = 0; s < ns; ++s) { uoff[s] = nu; nu += sn_h[s] - sn_w[s]; }
   bj->nu = nu;
+  // Update matrices ((h-w)^2 doubles each) live from their supernode's level to their PARENT's level only: offsets come
+  // from a first-fit allocator replayed level by level (allocate the level's own, free the children it consumed).  All
+  // of them at once would be 4x the factor itself (64^3 block: 4.2 GB against 1.2 GB live at the worst level; 128^3:
+  // ~76 GB against ~19 GB), which is what limited the blocks a GPU can factor, not the factor.
+  std::vector<std::vector<std::pair<long long, long long>>> s_zero(nlev);   // ranges born at a level: zeroed before use
+  {
+    std::map<long long, long long> freemap;   // offset -> length, coalesced
+    freemap[0] = (long long)1 << 60;
+    std::vector<std::vector<int>> kids_of(ns);
+    for (int s = 0; s < ns; ++s) if (sn_par[s] >= 0) kids_of[sn_par[s]].push_back(s);
+    auto release = [&](long long off, long long len) {
+      auto it = freemap.emplace(off, len).first;
+      auto nx = std::next(it);
+      if (nx != freemap.end() && it->first + it->second == nx->first) { it->second += nx->second; freemap.erase(nx); }
+      if (it != freemap.begin()) {
+        auto pv = std::prev(it);
+        if (pv->first + pv->second == it->first) { pv->second += it->second; freemap.erase(it); }
+      }
+    };
+    for (int l = 0; l < nlev; ++l) {
+      for (int q = lev_ptr[l]; q < lev_ptr[l + 1]; ++q) {
+        const int s = order[q];
+        const long long need = (long long)(sn_h[s] - sn_w[s]) * (sn_h[s] - sn_w[s]);
+        soff[s] = 0;
+        if (need == 0) continue;
+        auto it = freemap.begin();
+        while (it->second < need) ++it;   // the last hole is unbounded
+        soff[s] = it->first;
+        const long long rest = it->second - need, at = it->first + need;
+        freemap.erase(it);
+        if (rest > 0) freemap[at] = rest;
+        stot = std::max(stot, soff[s] + need);
+        if (!s_zero[l].empty() && s_zero[l].back().first + s_zero[l].back().second == soff[s]) s_zero[l].back().second += need;
+        else s_zero[l].push_back({soff[s], need});
+      }
+      for (int q = lev_ptr[l]; q < lev_ptr[l + 1]; ++q)
+        for (int c : kids_of[order[q]]) {
+          const long long len = (long long)(sn_h[c] - sn_w[c]) * (sn_h[c] - sn_w[c]);
+          if (len > 0) release(soff[c], len);
+        }
+    }
+    for (int l = 0; l < nlev; ++l) {   // fewer, larger memsets
+      auto& z = s_zero[l];
+      std::sort(z.begin(), z.end());
+      size_t o = 0;
+      for (size_t i = 1; i < z.size(); ++i) {
+        if (z[o].first + z[o].second == z[i].first) z[o].second += z[i].second;
+        else z[++o] = z[i];
+      }
+      if (!z.empty()) z.resize(o + 1);
+    }
+  }
+  bj->stat[10] = 8.0 * (double)stot;
   for (int l = 0; l < nlev; ++l) {
     long long z = 0, d = 0;
     for (int q = lev_ptr[l]; q < lev_ptr[l + 1]; ++q) {
@@ -752,7 +803,6 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   PCU_CUDA(cudaMalloc(&Dbuf, sizeof(double) * std::max<long long>(dmax, 1)));
   PCU_CUDA(cudaMalloc(&d_fail, sizeof(int)));
   PCU_CUDA(cudaMemset(d_fail, 0, sizeof(int)));
-  PCU_CUDA(cudaMemsetAsync(Sbuf, 0, sizeof(double) * std::max<long long>(stot, 1), ctx->stream));
   if (upload(&d_sn, h_sn) || upload(&d_aent, aent) || upload(&d_rel, rel)) return 1;
   PCU_CUDA(cudaMalloc(&bj->fwd_data, sizeof(double) * std::max<long long>(fdoubles, 1)));
   if (tcopy) PCU_CUDA(cudaMalloc(&bj->bwd_data, sizeof(double) * std::max<long long>(bdoubles, 1)));
@@ -787,6 +837,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       maxu = std::max(maxu, sn_h[s] - sn_w[s]);
     }
     PCU_CUDA(cudaMemsetAsync(Zbuf, 0, sizeof(double) * zl, st));
+    for (auto& z : s_zero[l]) PCU_CUDA(cudaMemsetAsync(Sbuf + z.first, 0, sizeof(double) * z.second, st));
     // 1. scatter the entries of A that live in this level's supernodes
     const long long na = aent_ptr[l + 1] - aent_ptr[l];
     if (na > 0) {

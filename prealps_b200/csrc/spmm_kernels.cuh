@@ -183,8 +183,21 @@ inline void pcu_trap() { std::abort(); }
 // and the sizes rounded up (the device arrays carry 16 bytes of slack at the end).  HALO = false (no column >= m: one
 // process, or the local part of the overlapped product) drops the "block row or halo row" select, so the row phase is
 // LDS + LDS + IMAD.WIDE + LDG + CPL DFMA per entry.  Needs ldx == T and every row block within the staging capacity.
+// gathers a lane issues back to back (row-loop unroll) against resident CTAs, measured on B200 (128^3, t = 8, us; profiles/
+// r02_spmm_occupancy.md): 4 columns per lane (7-point): unroll 4 at 40 registers / 6 CTAs per SM 101.9, unroll 8 at 48 / 5: 109.6,
+// unroll 2 at 32 / 8: 95.3 -- a full SM of threads beats more loads in flight per thread; 2 columns per lane keeps unroll 4
+#ifndef PCU_SPMM_MINB4
+#define PCU_SPMM_MINB4 8
+#endif
+#ifndef PCU_SPMM_UNROLL4
+#define PCU_SPMM_UNROLL4 2
+#endif
+#ifndef PCU_SPMM_UNROLL2
+#define PCU_SPMM_UNROLL2 4
+#endif
+constexpr int kRowUnroll4 = PCU_SPMM_UNROLL4, kRowUnroll2 = PCU_SPMM_UNROLL2;
 template <int T, int CPL, bool HALO>
-__global__ void __launch_bounds__(kThreads, CPL == 4 ? 6 : 8) spmm_bulk_kernel(SpmmArgs a) {  // <= 40 / 32 registers, no spills
+__global__ void __launch_bounds__(kThreads, CPL == 4 ? PCU_SPMM_MINB4 : 8) spmm_bulk_kernel(SpmmArgs a) {  // 32 registers, no spills
 
   static_assert(CPL == 2 || CPL == 4, "lanes own 2 or 4 adjacent columns");
   constexpr int G = T / CPL;
@@ -226,8 +239,7 @@ __global__ void __launch_bounds__(kThreads, CPL == 4 ? 6 : 8) spmm_bulk_kernel(S
     double acc[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) acc[j] = 0.0;
-#pragma unroll 4
-    for (int p = b; p < e; ++p) {
+    auto entry = [&](int p) {
       const int c = s_col[oc + p];
       const double v = s_val[ov + p];
       const double* src = ((HALO && c >= a.m) ? hl : xl) + (size_t)c * T;
@@ -241,6 +253,13 @@ __global__ void __launch_bounds__(kThreads, CPL == 4 ? 6 : 8) spmm_bulk_kernel(S
         acc[0] = fma(v, x.x, acc[0]);
         acc[1] = fma(v, x.y, acc[1]);
       }
+    };
+    if constexpr (CPL == 4) {
+#pragma unroll (kRowUnroll4)
+      for (int p = b; p < e; ++p) entry(p);
+    } else {
+#pragma unroll (kRowUnroll2)
+      for (int p = b; p < e; ++p) entry(p);
     }
     double* dst = a.Y + (size_t)r * a.ldy + CPL * lig;
     if constexpr (CPL == 4) {
