@@ -149,6 +149,32 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// warp-private ring of panel data in shared memory, filled by cp.async.bulk (SASS UBLKCP) issued by one lane, completion
+// on one mbarrier per stage
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_stream(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar,
+                                                unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_addr(smem)),
+               "l"(gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {  // bounded: a lost copy traps, it does not hang
+  unsigned ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(phase) : "memory");
+    if (ok) return;
+    if (++spins > (1u << 26)) __trap();
+  }
+}
 #else  // tests/emul: the same data movement without the cache hints; cp.async completes at once
 inline void ld_stream4(const double* p, double2& a, double2& b) {
   pcu_emul_check_aligned(p, 32);
@@ -165,15 +191,33 @@ inline void cp_async16_stream(void* smem_dst, const void* gmem_src, unsigned lon
 inline void cp_async_commit() {}
 template <int N>
 inline void cp_async_wait() {}
+inline void mbar_init(unsigned long long*, unsigned) {}
+inline void fence_mbar_init() {}
+inline void mbar_arrive_expect_tx(unsigned long long*, unsigned) {}
+inline void bulk_g2s_stream(void* smem, const void* gmem, unsigned bytes, unsigned long long*, unsigned long long) {
+  pcu_emul_check_aligned(smem, 16);
+  pcu_emul_check_aligned(gmem, 16);
+  std::memcpy(smem, gmem, bytes);
+}
+inline void mbar_wait(unsigned long long*, unsigned) {}
 #endif
 
 // rows of the input block staged per tile and per warp (4 KB per buffer at any T)
-template <int T, bool FWD>
-struct Tile {  // k steps per tile, even, KT*T*8 = 4 KB for T >= 8; the backward sweep consumes whole 32-row tiles of M
-  static constexpr int KT0 = (T <= 8) ? 64 : (512 / T);
-  static constexpr int KT = (!FWD && KT0 < 32) ? 32 : KT0;
+template <int T, bool STREAM>
+struct Tile {
+  // k steps of input rows per tile.  STREAM (contiguous panels, the shared-memory panel ring takes 8 KB per warp): 32 (16 from
+  // t = 16 up), KT*T*8 = 2 KB at t = 8 and 16; the tile-wise backward sweep of the single-copy factor keeps its panel data in
+  // registers, consumes whole 32-row tiles of M and stages 64 rows (4 KB at t = 8)
+  static constexpr int KT0 = STREAM ? ((T <= 8) ? 32 : 16) : ((T <= 8) ? 64 : (512 / T));
+  static constexpr int KT = (!STREAM && KT0 < 32) ? 32 : KT0;
 };
-
+// Shared-memory ring of panel data per warp: RS stages of RK k-blocks (1 KB each), one cp.async.bulk copy per stage.
+// Measured on B200 (128^3, 8 blocks / one 64^3 block, t = 8, apply in ms; profiles/r02_smem_ring.md): register ring of 4
+// k-blocks 3.507 / 0.754; shared-memory ring 8 x 1: 3.530 / 0.772; 4 x 2: 3.286 / 0.696; 2 x 4: 3.226 / 0.678 -- the bytes
+// in flight per warp double without a register spent on them (80 instead of 128 registers), and few large copies beat
+// many small ones; 3 CTAs/SM with 6 KB rings lose (3.242 / 0.737 and 3.624 / 0.828).
+template <int T>
+struct Ring { static constexpr int RK = (T <= 16) ? 4 : 2, RS = 2, DOUBLES = RK * RS * 128; };
 
 #ifndef PCU_EMUL
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -295,7 +339,6 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
   for (int rg = 0; rg < 4; ++rg)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
-  const double* base = a.data + off + lane * 4;   // forward: the panel; backward: the supernode's first slice
   const int* rows = a.rows + rows_off;
 
   // copy the input rows of steps [4*tq, 4*tq + KT) into buf (steps past the panel are clamped: their
@@ -328,48 +371,68 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
   };
 
   if constexpr (STREAM) {
-    double2 ring0[D], ring1[D];
-    auto issue = [&](int kb, double2& m0, double2& m1) {
-      if (kb < q1) {
-        const double* p = base + (size_t)kb * 128;
-        if (NOALLOC) ld_stream4(p, m0, m1);
-        else { m0 = __ldg(reinterpret_cast<const double2*>(p)); m1 = __ldg(reinterpret_cast<const double2*>(p + 2)); }
-      } else {
-        m0 = make_double2(0.0, 0.0);
-        m1 = m0;
+    // panel data through a warp-private shared-memory ring: RS stages of RK k-blocks, each stage one cp.async.bulk copy
+    // (SASS UBLKCP, L2 evict-first) issued by lane 0 and completed on its own mbarrier; the lanes read their A fragments
+    // from it with two conflict-free 16-byte loads per k-block (struct Ring)
+    constexpr int RK = Ring<T>::RK, RS = Ring<T>::RS;
+    static_assert(KB % RK == 0, "a tile is a whole number of ring stages");
+    double* ringbuf = smem + 32 * T + (size_t)kWarps * 2 * TILE + (size_t)warp * Ring<T>::DOUBLES;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 32 * T + (size_t)kWarps * 2 * TILE +
+                                                                     (size_t)kWarps * Ring<T>::DOUBLES) + warp * RS;
+    const unsigned long long pol = l2_evict_first_policy();
+    if (lane == 0) {
+#pragma unroll
+      for (int sg = 0; sg < RS; ++sg) mbar_init(bars + sg, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    const double* pdata = a.data + off;
+    int pk = q0;   // next k-block to fetch (lane 0)
+    auto refill = [&](int sg) {
+      if (pk < q1) {
+        const int nk = min(RK, q1 - pk);
+        mbar_arrive_expect_tx(bars + sg, (unsigned)nk * 1024u);
+        bulk_g2s_stream(ringbuf + (size_t)sg * RK * 128, pdata + (size_t)pk * 128, (unsigned)nk * 1024u, bars + sg, pol);
+        pk += nk;
       }
     };
     // panel data does not depend on the previous kernel: in flight before the wait
-    if (q0 < q1) {
+    if (lane == 0) {
 #pragma unroll
-      for (int u2 = 0; u2 < D; ++u2) issue(q0 + u2, ring0[u2], ring1[u2]);
+      for (int sg = 0; sg < RS; ++sg) refill(sg);
     }
     pdl_wait();
     pdl_launch_dependents();
     if (q0 < q1) {
       stage(q0, tile0);
-      int tix = 0;
+      int tix = 0, it = 0;
       for (int tq = q0; tq < q1; tq += KB, ++tix) {
         const double* cur = tile0 + (size_t)(tix & 1) * TILE;
         if (tq + KB < q1) { stage(tq + KB, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncwarp();
 #pragma unroll 1
-        for (int kq = 0; kq < KB; kq += D) {
+        for (int kq = 0; kq < KB && tq + kq < q1; kq += RK, ++it) {
+          const int sg = it % RS;
+          mbar_wait(bars + sg, (unsigned)(it / RS) & 1u);
 #pragma unroll
-          for (int u2 = 0; u2 < D; ++u2) {
-            const double2 m0 = ring0[u2], m1 = ring1[u2];
-            issue(tq + kq + u2 + D, ring0[u2], ring1[u2]);
-            const double* brow = cur + (size_t)(4 * (kq + u2) + lk) * T;
+          for (int u2 = 0; u2 < RK; ++u2) {
+            if (tq + kq + u2 < q1) {
+              const double* mp = ringbuf + (size_t)(sg * RK + u2) * 128 + lane * 4;
+              const double2 m0 = *reinterpret_cast<const double2*>(mp), m1 = *reinterpret_cast<const double2*>(mp + 2);
+              const double* brow = cur + (size_t)(4 * (kq + u2) + lk) * T;
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-              const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
-              dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
-              dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
-              dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
-              dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+              for (int nb = 0; nb < NB; ++nb) {
+                const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
+                dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
+                dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
+                dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
+                dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
+              }
             }
           }
+          __syncwarp();
+          if (lane == 0) refill(sg);
         }
         __syncwarp();
       }
@@ -525,12 +588,16 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
   const int nkb = STREAM ? (klen >> 2) : min(8, ((w + 3) >> 2) - 8 * qcol);
   const int* rows = a.rows + rows_off;
   const unsigned long long pol = l2_evict_first_policy();
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + (size_t)WARPS * (MB + BB)) + warp;
   if constexpr (STREAM) {
-    const double* base = a.data + off + lane * 4;
-    for (int kb = 0; kb < nkb; ++kb) {
-      cp_async16_stream(mbuf + kb * 128 + lane * 4, base + (size_t)kb * 128, pol);
-      cp_async16_stream(mbuf + kb * 128 + lane * 4 + 2, base + (size_t)kb * 128 + 2, pol);
+    // the whole panel with ONE cp.async.bulk copy (lane 0), completion on the warp's mbarrier
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(bar, (unsigned)nkb * 1024u);
+      bulk_g2s_stream(mbuf, a.data + off, (unsigned)nkb * 1024u, bar, pol);
     }
+    __syncwarp();
   } else {
     // lands in the lane order of the backward A fragments (bwd_lane_offset): unit jg, even steps then odd steps
     const double* base = a.data + off + panel_cum(w, qcol) + (long long)qcol * 1024 + bwd_lane_offset(lane);
@@ -578,6 +645,7 @@ __global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int
   cp_async_wait<0>();
   __syncwarp();
   if constexpr (STREAM) {
+    mbar_wait(bar, 0);
 #pragma unroll 2
     for (int kb = 0; kb < nkb; ++kb) {
       const double2 m0 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4);
@@ -659,7 +727,7 @@ void launch_chain(void (*kernel)(KArgs...), int grid, int block, size_t smem, cu
 
 template <int T, bool FWD, int D, bool NOALLOC, int OCC, bool TCOPY>
 void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
-  constexpr int bytes = (32 * T + kWarps * 2 * Tile<T, FWD || TCOPY>::KT * T) * (int)sizeof(double);
+  constexpr int bytes = (32 * T + kWarps * 2 * Tile<T, FWD || TCOPY>::KT * T + ((FWD || TCOPY) ? kWarps * (Ring<T>::DOUBLES + Ring<T>::RS) : 0)) * (int)sizeof(double);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(sweep_kernel<T, FWD, D, NOALLOC, OCC, TCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -670,7 +738,7 @@ void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
 
 template <int T, bool FWD, int KMAX, int WARPS, bool TCOPY>
 void launch_tiny_one(int first, int count, cudaStream_t st, const SweepArgs& a) {
-  constexpr int bytes = WARPS * (KMAX * 32 + KMAX * T) * (int)sizeof(double);
+  constexpr int bytes = WARPS * (KMAX * 32 + KMAX * T + 1) * (int)sizeof(double);   // + one mbarrier per warp
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(sweep_tiny_kernel<T, FWD, KMAX, WARPS, TCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
