@@ -107,8 +107,9 @@ int pcu_spmm_halo_exchange(pcu_spmm* op, const double* X, int ldx, int t);
 int pcu_spmm_halo_pack(pcu_spmm* op, const double* X, int ldx, int t, double** packed_dev, int* nrows);
 double* pcu_spmm_halo_buffer(pcu_spmm* op, int t);   /* device pointer to H (nhalo x t, ld = t) */
 int pcu_spmm_apply(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, int t);
-/* pcu_spmm_halo_exchange + pcu_spmm_apply in one call (NCCL transport); with PREALPS_SPMM_OVERLAP=1 the exchange runs next to
- * the local part of the product, like MPI_Isend / diagonal block / MPI_Irecv of ref: cplm_v0_matmult_v2.c:182-276 */
+/* pcu_spmm_halo_exchange + pcu_spmm_apply in one call (NCCL transport): the exchange runs next to the local part of the
+ * product, like MPI_Isend / diagonal block / MPI_Irecv of ref: cplm_v0_matmult_v2.c:182-276 (PREALPS_SPMM_OVERLAP=0 when the
+ * operator is created: one after the other) */
 int pcu_spmm_apply_exchange(pcu_spmm* op, const double* X, int ldx, double* Y, int ldy, int t);
 /* algorithmic bytes of one apply at block width t */
 double pcu_spmm_bytes(pcu_spmm* op, int t);

@@ -677,7 +677,13 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     }
     bj->scratch_slots = std::max(bj->scratch_slots, slots);
     bj->ncounters = std::max(bj->ncounters, ctrs);
-    while (i < count) { const int c = std::min(8, count - i); units.push_back({first + i, c, 0, 0, 0, 0, 1, 0, 0, 0}); i += c; }
+    // the other panels: one warp per panel, and when a level has many more panels than the machine has warp slots a warp
+    // takes several in a row (first + warp, + 8, + 16, ...: the sweep kernel streams across them, bj_solve.cu) -- as many as
+    // leave every CTA slot several units.  Not for the tile-wise backward sweep of the single-copy factor.
+    const int pw_max = getenv("PREALPS_BJ_PW") ? atoi(getenv("PREALPS_BJ_PW")) : 4;
+    const int pw_force = getenv("PREALPS_BJ_PW_FORCE") ? atoi(getenv("PREALPS_BJ_PW_FORCE")) : 0;   // tests
+    const int pw = tiles ? 1 : pw_force > 0 ? pw_force : std::max(1, std::min(pw_max, (count - i) / (8 * 148 * 2 * 2)));
+    while (i < count) { const int c = std::min(8 * pw, count - i); units.push_back({first + i, c, 0, 0, 0, 0, 1, 0, 0, 0}); i += c; }
     // CTAs are dispatched in unit order: longest first by TIME, not by panel length.  A CTA whose 8 warps each stream a
     // whole panel of just under split_kb k-blocks runs as long as a CTA that shares a panel 8 times as long; left at
     // the end of the list (they were, the list being sorted by panel length) those groups were the tail of every level.
@@ -685,7 +691,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       auto cost = [&](const WorkUnit& u) {
         if (u.split == 2) return (u.kb1 - u.kb0 + 7) / 8;
         if (u.split == 1) return (cost_kb(u.first) + 7) / 8;
-        return cost_kb(u.first);  // the first panel of a group is its longest
+        return cost_kb(u.first) * ((u.count + 7) / 8);  // the first panel of a group is its longest
       };
       std::stable_sort(units.begin() + u_begin, units.end(), [&](const WorkUnit& a, const WorkUnit& b) { return cost(a) > cost(b); });
     }

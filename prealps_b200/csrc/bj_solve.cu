@@ -317,14 +317,18 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
   const int pidx = u.split ? u.first : u.first + warp;
   long long off;
   int klen, c0, w, h, row0;
-  long long uoff = 0, rows_off = 0;
-  if (FWD) {
-    const FwdPanel p = reinterpret_cast<const FwdPanel*>(a.panels)[pidx];
-    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.row0; uoff = p.uoff;
-  } else {
-    const BwdPanel p = reinterpret_cast<const BwdPanel*>(a.panels)[pidx];
-    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
-  }
+  long long uoff = 0;
+  const int* rows = a.rows;
+  auto load_desc = [&](int idx) {
+    if (FWD) {
+      const FwdPanel p = reinterpret_cast<const FwdPanel*>(a.panels)[idx];
+      off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.row0; uoff = p.uoff;
+    } else {
+      const BwdPanel p = reinterpret_cast<const BwdPanel*>(a.panels)[idx];
+      off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows = a.rows + p.rows_off;
+    }
+  };
+  load_desc(pidx);
   const int nkb = klen >> 2;
   int q0 = 0, q1 = nkb;
   if (u.split) {
@@ -339,7 +343,6 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
   for (int rg = 0; rg < 4; ++rg)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
-  const int* rows = a.rows + rows_off;
 
   // copy the input rows of steps [4*tq, 4*tq + KT) into buf (steps past the panel are clamped: their
   // panel entries are zero padding)
@@ -386,15 +389,26 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
       fence_mbar_init();
     }
     __syncwarp();
+    // A warp that owns a whole panel goes on to the warp's next panels (u.first + warp + 8, + 16, ...): lane 0 keeps
+    // the ring filled ACROSS panels (a stage never mixes two panels) and the first input tile of the next panel is staged
+    // during the last tile of the current one, so the chain "descriptor -> first panel data -> gather indices -> input
+    // rows" is paid once per warp, not once per panel (the short panels of the lower half of the forest are a few
+    // microseconds of streaming each).
+    const int pidx_end = u.split ? 0 : u.first + u.count;
     const double* pdata = a.data + off;
-    int pk = q0;   // next k-block to fetch (lane 0)
+    int pk = q0, pend = q1, pnext = pidx + kWarps;   // producer (lane 0): next k-block to fetch, end, the panel after
     auto refill = [&](int sg) {
-      if (pk < q1) {
-        const int nk = min(RK, q1 - pk);
-        mbar_arrive_expect_tx(bars + sg, (unsigned)nk * 1024u);
-        bulk_g2s_stream(ringbuf + (size_t)sg * RK * 128, pdata + (size_t)pk * 128, (unsigned)nk * 1024u, bars + sg, pol);
-        pk += nk;
+      if (pk >= pend) {
+        if (pnext >= pidx_end) return;
+        long long noff; int nklen;
+        if (FWD) { const FwdPanel* np = reinterpret_cast<const FwdPanel*>(a.panels) + pnext; noff = __ldg(&np->off); nklen = __ldg(&np->klen); }
+        else { const BwdPanel* np = reinterpret_cast<const BwdPanel*>(a.panels) + pnext; noff = __ldg(&np->off); nklen = __ldg(&np->klen); }
+        pdata = a.data + noff; pk = 0; pend = nklen >> 2; pnext += kWarps;
       }
+      const int nk = min(RK, pend - pk);
+      mbar_arrive_expect_tx(bars + sg, (unsigned)nk * 1024u);
+      bulk_g2s_stream(ringbuf + (size_t)sg * RK * 128, pdata + (size_t)pk * 128, (unsigned)nk * 1024u, bars + sg, pol);
+      pk += nk;
     };
     // panel data does not depend on the previous kernel: in flight before the wait
     if (lane == 0) {
@@ -405,11 +419,21 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
     pdl_launch_dependents();
     if (q0 < q1) {
       stage(q0, tile0);
-      int tix = 0, it = 0;
+      int tix = 0, it = 0, cidx = pidx;
+      for (;;) {
+      int s_row0 = row0, s_c0 = c0, s_w = w, s_h = h;   // what storing this panel's results needs
+      long long s_uoff = uoff;
+      bool more = false;
       for (int tq = q0; tq < q1; tq += KB, ++tix) {
         const double* cur = tile0 + (size_t)(tix & 1) * TILE;
         if (tq + KB < q1) { stage(tq + KB, tile0 + (size_t)((tix + 1) & 1) * TILE); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        else if (cidx + kWarps < pidx_end) {   // last tile: the first input tile of the warp's next panel
+          cidx += kWarps;
+          load_desc(cidx);
+          stage(0, tile0 + (size_t)((tix + 1) & 1) * TILE);
+          more = true;
+          cp_async_wait<1>();
+        } else cp_async_wait<0>();
         __syncwarp();
 #pragma unroll 1
         for (int kq = 0; kq < KB && tq + kq < q1; kq += RK, ++it) {
@@ -435,6 +459,15 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
           if (lane == 0) refill(sg);
         }
         __syncwarp();
+      }
+      if (u.split) break;
+      store_outputs<T, FWD>(acc, a, s_row0, s_c0, s_w, s_h, s_uoff, lr, lk);
+      if (!more) return;
+      q0 = 0; q1 = klen >> 2;
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
       }
     }
   } else {

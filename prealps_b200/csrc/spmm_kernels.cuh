@@ -331,7 +331,7 @@ __global__ void halo_pack_kernel(const double* __restrict__ X, int ldx, int t, c
   }
 }
 
-// Overlapped product (opt-in, PREALPS_SPMM_OVERLAP=1): Y[r, :] += sum_k hval[k] * H[hcol[k], :] for the rows that read
+// Overlapped product (the default under NCCL; PREALPS_SPMM_OVERLAP=0 serialises): Y[r, :] += sum_k hval[k] * H[hcol[k], :] for the rows that read
 // halo rows, after the local kernel has written the partial sums of the entries with column < m.  Halo columns sort
 // after the local ones, so continuing each row's FMA chain from the stored partial sum reproduces the merged kernel's
 // summation order bit for bit.  16 lanes per row, lane owns columns lig and lig + 16 (any t <= 32).

@@ -58,12 +58,16 @@ def direct(blocks, cuts, B):
     return np.vstack([spla.splu(Bk.tocsc()).solve(B[cuts[b]:cuts[b + 1]]) for b, Bk in enumerate(blocks)])
 
 
-@pytest.mark.parametrize("gen,N,nblk,ts,copies", [("poisson7", 5, 1, (1, 8), 2), ("poisson7", 6, 2, (16, 4, 8), 1),
-                                                    ("stencil27", 4, 1, (3, 8, 2), 2), ("poisson7", 9, 1, (8, 32, 3), 1)])
-def test_factor_and_solve_match_direct_solver(emul, gen, N, nblk, ts, copies, monkeypatch):
+@pytest.mark.parametrize("gen,N,nblk,ts,copies,pw", [("poisson7", 5, 1, (1, 8), 2, 0), ("poisson7", 6, 2, (16, 4, 8), 1, 0),
+                                                       ("stencil27", 4, 1, (3, 8, 2), 2, 2), ("poisson7", 9, 1, (8, 32, 3), 1, 0),
+                                                       ("poisson7", 9, 1, (8, 16, 1), 2, 3)])
+def test_factor_and_solve_match_direct_solver(emul, gen, N, nblk, ts, copies, pw, monkeypatch):
     """copies = 2: the factor keeps the transposed panels; copies = 1: the backward sweep reads the forward panels tile by
-    tile (bj.h).  poisson7 9^3 has supernodes wider and taller than one 32 x 32 tile."""
+    tile (bj.h).  poisson7 9^3 has supernodes wider and taller than one 32 x 32 tile.  pw > 0 forces that many panels per
+    warp (the sweep kernel streams across them; the planner only does this on levels with tens of thousands of panels)."""
     monkeypatch.setenv("PREALPS_BJ_COPIES", str(copies))
+    if pw:
+        monkeypatch.setenv("PREALPS_BJ_PW_FORCE", str(pw))
     lib, ctx = emul
     A = getattr(gen_matrices, gen)(N).tocsr()
     n = A.shape[0]
