@@ -109,6 +109,81 @@ __global__ void __launch_bounds__(kThreads, NB == 16 ? 2 : 4) assemble_kernel(co
   }
 }
 
+// The same assembly for the levels whose columns gather long lists (the top of the forest: hundreds of update rows per column,
+// few columns): one WARP per column.  The 32 / G lane groups of the warp take the batches of NB rows round robin (32 / G * NB
+// rows of a column in flight instead of 16, the chain of dependent round trips that an assembly launch there consists of is
+// 32 / G times shorter), then add their partial sums in a fixed order (xor butterfly): bit-reproducible, not bit-identical to
+// the sequential order of assemble_kernel.
+template <int T>
+__global__ void __launch_bounds__(kThreads, 4) assemble_wide_kernel(const int* __restrict__ cols, int ncols,
+                                                                    const double* __restrict__ B, int ldb, int t,
+                                                                    const int* __restrict__ perm,
+                                                                    const long long* __restrict__ gl_ptr,
+                                                                    const long long* __restrict__ gl_idx,
+                                                                    const double* __restrict__ U, long long pad,
+                                                                    double* __restrict__ Wk) {
+  constexpr int CPL = (T >= 2) ? 2 : 1;
+  constexpr int G = T / CPL;      // lanes per row
+  constexpr int SG = 32 / G;      // lane groups per warp
+  constexpr int NB = 8;
+  const int lane = threadIdx.x & 31, sub = lane / G, lig = lane % G;
+  const int wq = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  int c_first = 0, row_first = 0;
+  long long g_first = 0, g1_first = 0;
+  long long idx[NB];
+  if (wq < ncols) {
+    c_first = __ldg(cols + wq);
+    row_first = __ldg(perm + c_first);
+    g_first = __ldg(gl_ptr + c_first);
+    g1_first = __ldg(gl_ptr + c_first + 1);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) idx[j] = (g_first + sub * NB + j < g1_first) ? __ldg(gl_idx + g_first + sub * NB + j) : pad;
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int q = wq; q < ncols; q += nwarps) {
+    const bool pre = (q == wq);
+    const int c = pre ? c_first : cols[q];
+    const int c0 = CPL * lig;
+    double a0 = 0.0, a1 = 0.0;
+    if (sub == 0) {
+      const double* src = B + (size_t)(pre ? row_first : perm[c]) * ldb;
+      if (c0 < t) a0 = src[c0];
+      if (CPL == 2 && c0 + 1 < t) a1 = src[c0 + 1];
+    }
+    const long long g0 = pre ? g_first : gl_ptr[c];
+    const long long g1 = pre ? g1_first : gl_ptr[c + 1];
+    if (!pre) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) idx[j] = (g0 + sub * NB + j < g1) ? __ldg(gl_idx + g0 + sub * NB + j) : pad;
+    }
+    for (long long g = g0 + sub * NB; g < g1; g += SG * NB) {
+      double2 v[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const double* u = U + (size_t)idx[j] * T + c0;
+        if (CPL == 2) v[j] = *reinterpret_cast<const double2*>(u);
+        else v[j] = make_double2(u[0], 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) idx[j] = (g + SG * NB + j < g1) ? __ldg(gl_idx + g + SG * NB + j) : pad;  // next batch
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { a0 += v[j].x; a1 += v[j].y; }
+    }
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (sub == 0) {
+      double* dst = Wk + (size_t)c * T + c0;
+      if (CPL == 2) *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
+      else dst[0] = a0;
+    }
+  }
+}
+
 struct SweepArgs {
   const WorkUnit* units;
   const void* panels;
@@ -287,16 +362,17 @@ __device__ __forceinline__ void store_outputs(const double (&acc)[4][(T + 7) / 8
   }
 }
 
-// One warp per short panel, or the 8 warps of a CTA on disjoint k ranges of one long panel.
-// Per warp and k-block (4 steps): 1 KB of the panel (32 B per lane, already in A-fragment order), one
-// shared-memory double per lane (B fragment of the T-wide input rows) and 4 DMMA per 8 output columns.
-//   (1) a ring of D k-blocks of panel data is always in flight (HBM latency),
+// One warp per short panel (and on levels with many short panels several panels in a row), or the 8 warps of a CTA on
+// disjoint k ranges of one long panel.  Per warp and k-block (4 steps): 1 KB of the panel (32 B per lane, already in
+// A-fragment order), one shared-memory double per lane (B fragment of the T-wide input rows) and 4 DMMA per 8 output columns.
+//   (1) panel data: a warp-private shared-memory ring of 2 stages x 4 k-blocks filled by cp.async.bulk (struct Ring), always
+//       8 KB in flight per warp (HBM latency) without a register spent on it; the tile-wise backward sweep of the
+//       single-copy factor keeps a register ring of two 2 KB units,
 //   (2) the input rows of the next tile of k steps are copied into a warp-private shared-memory buffer with
 //       cp.async while the current tile is consumed,
-//   (3) the accumulators are 2 doubles per 8x8 block (8 doubles at T = 8), which keeps the register budget for
-//       the ring: 3 CTAs/SM = 24 warps x 4 KB in flight.
+//   (3) the accumulators are 2 doubles per 8x8 block (8 doubles at T = 8).
 // History (128^3, t=8, whole apply): plain FMA loop 2.1 TB/s (long-scoreboard bound), + register ring 2.6,
-// + cp.async tiles 3.5, DMMA + fragment-order panels: see profiles/.
+// + cp.async tiles 3.5, DMMA + fragment-order panels 4.3 ... 5.2, shared-memory ring 5.7: see profiles/.
 // TCOPY (backward only): the factor also holds the transposed panels (bj.h), the backward sweep streams them exactly like
 // the forward sweep streams M; without them it reads M tile by tile.
 template <int T, bool FWD, int D, bool NOALLOC, int OCC, bool TCOPY>
@@ -306,7 +382,6 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
   constexpr int KT = Tile<T, STREAM>::KT;  // k steps per input tile
   constexpr int KB = KT / 4;            // k-blocks per tile
   constexpr int TILE = KT * T;          // doubles per tile buffer
-  static_assert(KB % D == 0, "ring depth must divide the k-blocks of a tile");
   PCU_DYN_SMEM(smem);
   double* red = smem;                   // 32 * T doubles
   const WorkUnit u = a.units[blockIdx.x];
@@ -846,6 +921,8 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
   a.scratch = bj->scratch; a.counters = bj->counters;
   // level 0 = the leaves: nothing to gather, so the forward panels read B[perm] themselves when the caller's rows can
   // be copied T wide in 16-byte pieces (t == T, even leading dimension, aligned base)
+  const char* asm_wide_env = getenv("PREALPS_BJ_ASM_WIDE");
+  const int asm_wide = asm_wide_env ? atoi(asm_wide_env) : 1;
   static const bool leaf_direct_on = getenv("PREALPS_BJ_NO_LEAF_DIRECT") == nullptr;
   const bool leaf_direct = leaf_direct_on && t == T && (T == 1 || (ldb % 2 == 0 && (reinterpret_cast<size_t>(B) & 15) == 0));
   for (int l = 0; l < bj->nlevels; ++l) {
@@ -855,7 +932,12 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
     if (ncols > 0 && a.Bsrc == nullptr) {
       prof.mark("asm L" + std::to_string(l) + " cols=" + std::to_string(ncols), 3.0 * ncols * T * 8);
       const int grid = stream_grid(c, (long long)ncols * G, kThreads, 8);
-      if (bj->lvl_long_lists[l])
+      // one warp per column where the lists are long AND the columns few (one subdomain per GPU: 0.683 -> 0.671 ms per apply);
+      // with tens of thousands of columns the 4-lane kernel already fills the machine and is 0.7 % faster (8 blocks per GPU)
+      if ((bj->lvl_long_lists[l] && ncols <= 8192 && asm_wide) || asm_wide == 2)   // 2: every level (tests)
+        launch_chain(assemble_wide_kernel<T>, stream_grid(c, (long long)ncols * 32, kThreads, 8), kThreads, 0, st,
+                     bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t, bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, pad, bj->Wk);
+      else if (bj->lvl_long_lists[l])
         launch_chain(assemble_kernel<T, 16>, grid, kThreads, 0, st, bj->lvl_cols + bj->lvl_col_ptr[l], ncols, B, ldb, t,
                      bj->perm, bj->gl_ptr, bj->gl_idx, bj->U, pad, bj->Wk);
       else

@@ -83,6 +83,12 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, int delta) {
   return (lane + delta < 32) ? (T)all[lane + delta] : v;
 }
 
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int mask) {
+  double all[32];
+  emul_warp_allgather((double)v, all);
+  return (T)all[((int)(threadIdx.x & 31) ^ mask) & 31];
+}
+
 inline void pcu_emul_check_aligned(const void* p, size_t a) {
   if (reinterpret_cast<uintptr_t>(p) % a != 0) {
     std::fprintf(stderr, "[emul] misaligned %zu-byte vector access at %p\n", a, p);

@@ -205,9 +205,10 @@ def test_block_jacobi_factor_and_solve(dev, gen, N, nblk, t, copies, monkeypatch
     """pcu_bj_create + pcu_bj_apply against a direct sparse solve of every diagonal block; with the transposed copy of the
     panels (copies = 2) and with the backward sweep reading the forward panels tile by tile (copies = 1)"""
     import scipy.sparse.linalg as spla
-    if copies == 23:   # two copies, three panels per warp forced: the sweep kernel streams across a warp's panels
-        copies = 2
+    if copies == 23:   # two copies, three panels per warp forced (the sweep kernel streams across a warp's panels) and the
+        copies = 2     # warp-per-column assembly on every level
         monkeypatch.setenv("PREALPS_BJ_PW_FORCE", "3")
+        monkeypatch.setenv("PREALPS_BJ_ASM_WIDE", "2")
     monkeypatch.setenv("PREALPS_BJ_COPIES", str(copies))
     A = getattr(gen_matrices, gen)(N).tocsr()
     n = A.shape[0]
