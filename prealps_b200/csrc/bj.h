@@ -60,12 +60,7 @@ struct BwdPanel {      // one 32-row slice of M_s^T = 32 columns of M_s
   int pad_;
 };
 
-constexpr int kTinyS = 16;  // ... and the very short ones get half of the buffer, 2x more warps per SM
-constexpr int kTinyK = 32;  // panels up to this many steps are staged whole into shared memory (64 was 3 % slower:
-                            // 20 KB of landing buffer per warp leaves 8 warps per SM)
-
 constexpr int kChunkMinKB = 128;            // shortest slice (k-blocks of 4 steps) a CTA gets when a long panel is cut across CTAs
-constexpr int kTinyFold = 512;              // fewer short panels than this at a level: no separate launch for them
 constexpr int kWarpSlots = 148 * 2 * 8;     // resident warps of the sweep kernel (2 CTAs of 8 warps per SM)
 
 struct WorkUnit {      // one CTA of the sweep kernels
@@ -98,10 +93,6 @@ struct pcu_bj {
   pcu::WorkUnit* bwd_units = nullptr;
   std::vector<int> fwd_unit_ptr, bwd_unit_ptr;   // per level, nlevels+1
   std::vector<double> fwd_lvl_bytes, bwd_lvl_bytes;    // panel bytes per level (profiling)
-  std::vector<double> fwd_tiny_bytes, bwd_tiny_bytes;  // of which in the tiny-panel launches
-  // panels with klen <= kTinyK at the end of each level's (klen-descending) list go to the tiny-panel kernel
-  std::vector<int> fwd_tiny0, fwd_tinyn, bwd_tiny0, bwd_tinyn;
-  std::vector<int> fwd_tinys, bwd_tinys;  // of those, the last *_tinys panels have klen <= kTinyS
   // device: assembly of the forward right-hand side
   int* perm = nullptr;             // perm[forest col] = local row of the m x t block
   int* rows = nullptr;             // forest row index of every supernode row (gather index of the backward sweep)

@@ -608,35 +608,21 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
   bj->fwd_unit_ptr.assign(nlev + 1, 0);
   bj->fwd_lvl_bytes.assign(nlev, 0.0);
   bj->bwd_lvl_bytes.assign(nlev, 0.0);
-  bj->fwd_tiny_bytes.assign(nlev, 0.0);
-  bj->bwd_tiny_bytes.assign(nlev, 0.0);
   bj->bwd_unit_ptr.assign(nlev + 1, 0);
   std::vector<std::vector<PackTask>> pk_f(nlev), pk_b(nlev);
   long long fdoubles = 0, bdoubles = 0;
   std::vector<long long> sn_doff(ns, 0);  // the panels of a supernode are contiguous, slice after slice (bj.h: panel_cum)
   const int kSplitK = 512;  // without level-adaptive cuts (PREALPS_BJ_NOCHUNK): panels at least this long get a whole CTA
-  bj->fwd_tiny0.assign(nlev, 0); bj->fwd_tinyn.assign(nlev, 0);
-  bj->bwd_tiny0.assign(nlev, 0); bj->bwd_tinyn.assign(nlev, 0);
-  bj->fwd_tinys.assign(nlev, 0); bj->bwd_tinys.assign(nlev, 0);
-  const bool use_tiny = getenv("PREALPS_BJ_NOTINY") == nullptr;
   const bool use_chunks = getenv("PREALPS_BJ_NOCHUNK") == nullptr;
   // klen_of: steps of a panel rounded to whole k-blocks (the backward kernel walks whole 32-row tiles: its slices are
   // cut at multiples of 8 k-blocks)
-  auto make_units = [&](std::vector<int>& klen_of, bool tiles, int first, int count_all, std::vector<WorkUnit>& units,
-                        int* tiny0, int* tinyn, int* tinys) {
+  // Every panel of a level goes to the one sweep launch of that level and direction.  (Until round 2 the panels of <= 32
+  // steps -- the leaves of the forest -- had a kernel of their own that staged a whole panel in shared memory; once the sweep
+  // kernel streamed its panel data through a shared-memory ring and across the panels of a warp, folding them into the regular
+  // launch was faster: 0.670 -> 0.641 ms for one 64^3 block, 3.190 -> 3.154 ms for eight; profiles/r02_smem_ring.md.)
+  auto make_units = [&](std::vector<int>& klen_of, bool tiles, int first, int count, std::vector<WorkUnit>& units) {
     auto cost_kb = [&](int i) { return klen_of[i] / 4; };
-    int count = count_all;
     const size_t u_begin = units.size();
-    if (use_tiny) while (count > 0 && klen_of[first + count - 1] <= kTinyK) --count;
-    // a handful of short panels next to longer ones ride along in the main launch (one warp each) instead of
-    // costing the level another one or two launches
-    static const int tiny_fold = getenv("PREALPS_BJ_TINYFOLD") ? atoi(getenv("PREALPS_BJ_TINYFOLD")) : kTinyFold;
-    if (count > 0 && count_all - count < tiny_fold) count = count_all;
-    *tiny0 = first + count;
-    *tinyn = count_all - count;
-    int cs = count_all;
-    while (!tiles && cs > count && klen_of[first + cs - 1] <= kTinyS) --cs;   // a backward slice always lands a whole tile
-    *tinys = count_all - cs;
     // panels [first, first+count) are already sorted by cost descending
     int i = 0;
     int slots = 0, ctrs = 0;
@@ -723,8 +709,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
     }
     kl.resize(fp.size());
     for (size_t i = f0; i < fp.size(); ++i) kl[i] = fp[i].klen;
-    make_units(kl, false, f0, (int)fp.size() - f0, fu, &bj->fwd_tiny0[l], &bj->fwd_tinyn[l], &bj->fwd_tinys[l]);
-    for (int i = bj->fwd_tiny0[l]; i < bj->fwd_tiny0[l] + bj->fwd_tinyn[l]; ++i) bj->fwd_tiny_bytes[l] += 8.0 * kl[i] * 32;
+    make_units(kl, false, f0, (int)fp.size() - f0, fu);
     bj->fwd_unit_ptr[l + 1] = (int)fu.size();
     // backward: slice q of M_s^T = the 32 columns [32q, 32q + 32) of the SAME panels, walked tile by tile (32 rows of
     // forward slice p = q, q+1, ...); klen counts rows, whole tiles
@@ -758,8 +743,7 @@ int pcu_bj_create(pcu_ctx* ctx, int nblk, const int* blk_ptr, const int* const* 
       size_t i = b0;
       for (auto& e : lst) kl[i++] = e.first;   // the exact length decides who shares a CTA and what is cut
     }
-    make_units(kl, !tcopy, b0, (int)bp.size() - b0, bu, &bj->bwd_tiny0[l], &bj->bwd_tinyn[l], &bj->bwd_tinys[l]);
-    for (int i = bj->bwd_tiny0[l]; i < bj->bwd_tiny0[l] + bj->bwd_tinyn[l]; ++i) bj->bwd_tiny_bytes[l] += bbytes[i - b0];
+    make_units(kl, !tcopy, b0, (int)bp.size() - b0, bu);
     bj->bwd_unit_ptr[l + 1] = (int)bu.size();
   }
   bj->fwd_doubles = fdoubles;

@@ -213,10 +213,6 @@ __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ void cp_async16_stream(void* smem_dst, const void* gmem_src, unsigned long long pol) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -262,7 +258,6 @@ inline void cp_async16(void* smem_dst, const void* gmem_src) {
   pcu_emul_check_aligned(gmem_src, 16);
   std::memcpy(smem_dst, gmem_src, 16);
 }
-inline void cp_async16_stream(void* smem_dst, const void* gmem_src, unsigned long long) { cp_async16(smem_dst, gmem_src); }
 inline void cp_async_commit() {}
 template <int N>
 inline void cp_async_wait() {}
@@ -664,132 +659,6 @@ __global__ void __launch_bounds__(kThreads, (T <= 8) ? OCC : ((T == 32 && !FWD &
   store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
 }
 
-// Tiny panels (klen <= kTinyK steps, the leaves of the elimination forest: most of the supernodes but ~10 % of
-// the data): one warp per panel, the WHOLE panel (<= 16 KB) and its input rows are copied to shared memory with
-// cp.async in one go, so 20 KB per warp are in flight and there is no per-tile latency chain; 4 warps per CTA.
-template <int T, bool FWD, int KMAX, int WARPS, bool TCOPY>
-__global__ void __launch_bounds__(WARPS * 32) sweep_tiny_kernel(SweepArgs a, int first, int count) {
-  constexpr bool STREAM = FWD || TCOPY;
-  constexpr int NB = (T + 7) / 8;
-  constexpr int MB = KMAX * 32;         // doubles of panel data per warp
-  constexpr int BB = KMAX * T;          // doubles of input rows per warp
-  PCU_DYN_SMEM(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lr = lane >> 2, lk = lane & 3;
-  const int q = blockIdx.x * WARPS + warp;
-  if (q >= count) return;
-  double* mbuf = smem + (size_t)warp * (MB + BB);
-  double* bbuf = mbuf + MB;
-  long long off;
-  int klen, c0, w, h, row0;
-  long long uoff = 0, rows_off = 0;
-  if (FWD) {
-    const FwdPanel p = reinterpret_cast<const FwdPanel*>(a.panels)[first + q];
-    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.row0; uoff = p.uoff;
-  } else {
-    const BwdPanel p = reinterpret_cast<const BwdPanel*>(a.panels)[first + q];
-    off = p.off; klen = p.klen; c0 = p.c0; w = p.w; h = p.h; row0 = p.k0; rows_off = p.rows_off;
-  }
-  // forward: the whole panel; backward: the k-blocks of the slice's 32 columns in the supernode's LAST forward slice
-  // (a one-tile backward slice: row0 = 32 * (slices - 1))
-  const int qcol = row0 >> 5;
-  const int nkb = STREAM ? (klen >> 2) : min(8, ((w + 3) >> 2) - 8 * qcol);
-  const int* rows = a.rows + rows_off;
-  const unsigned long long pol = l2_evict_first_policy();
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + (size_t)WARPS * (MB + BB)) + warp;
-  if constexpr (STREAM) {
-    // the whole panel with ONE cp.async.bulk copy (lane 0), completion on the warp's mbarrier
-    if (lane == 0) {
-      mbar_init(bar, 1);
-      fence_mbar_init();
-      mbar_arrive_expect_tx(bar, (unsigned)nkb * 1024u);
-      bulk_g2s_stream(mbuf, a.data + off, (unsigned)nkb * 1024u, bar, pol);
-    }
-    __syncwarp();
-  } else {
-    // lands in the lane order of the backward A fragments (bwd_lane_offset): unit jg, even steps then odd steps
-    const double* base = a.data + off + panel_cum(w, qcol) + (long long)qcol * 1024 + bwd_lane_offset(lane);
-    for (int jg = 0; 2 * jg < nkb; ++jg)
-      for (int par = 0; par < 2; ++par) {
-        double* dst = mbuf + ((2 * jg + par) * 32 + lane) * 4;
-        if (2 * jg + (lane >> 4) < nkb) {
-          const double* src = base + (size_t)(2 * jg) * 128 + 64 * par;
-          cp_async16_stream(dst, src, pol);
-          cp_async16_stream(dst + 2, src + 2, pol);
-        } else {
-          dst[0] = dst[1] = dst[2] = dst[3] = 0.0;
-        }
-      }
-  }
-  pdl_wait();   // the panel itself is static; the input rows come from the previous kernel
-  pdl_launch_dependents();
-  if (T >= 2) {
-    constexpr int CPR = (T >= 2) ? T / 2 : 1;
-    const int chunks = klen * CPR;
-    for (int qq = lane; qq < chunks; qq += 32) {
-      const int r = qq / CPR, part = qq % CPR;
-      const double* src;
-      if (FWD) src = a.Bsrc ? a.Bsrc + (size_t)__ldg(a.perm + c0 + r) * a.ldb : a.Wk + (size_t)(c0 + r) * T;
-      else {
-        const int i = min(row0 + r, h - 1);
-        src = (i < w) ? a.Y + (size_t)(c0 + i) * T : a.Xp + (size_t)__ldg(rows + i) * T;
-      }
-      cp_async16(bbuf + (size_t)r * T + 2 * part, src + 2 * part);
-    }
-  } else {
-    for (int r = lane; r < klen; r += 32) {
-      const double* src;
-      if (FWD) src = a.Bsrc ? a.Bsrc + (size_t)__ldg(a.perm + c0 + r) * a.ldb : a.Wk + (size_t)(c0 + r);
-      else { const int i = min(row0 + r, h - 1); src = (i < w) ? a.Y + (size_t)(c0 + i) : a.Xp + (size_t)__ldg(rows + i); }
-      bbuf[r] = *src;
-    }
-  }
-  cp_async_commit();
-  double acc[4][NB][2];
-#pragma unroll
-  for (int rg = 0; rg < 4; ++rg)
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) acc[rg][nb][0] = acc[rg][nb][1] = 0.0;
-  cp_async_wait<0>();
-  __syncwarp();
-  if constexpr (STREAM) {
-    mbar_wait(bar, 0);
-#pragma unroll 2
-    for (int kb = 0; kb < nkb; ++kb) {
-      const double2 m0 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4);
-      const double2 m1 = *reinterpret_cast<const double2*>(mbuf + kb * 128 + lane * 4 + 2);
-      const double* brow = bbuf + (size_t)(4 * kb + lk) * T;
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
-        dmma884(acc[0][nb][0], acc[0][nb][1], m0.x, bf);
-        dmma884(acc[1][nb][0], acc[1][nb][1], m0.y, bf);
-        dmma884(acc[2][nb][0], acc[2][nb][1], m1.x, bf);
-        dmma884(acc[3][nb][0], acc[3][nb][1], m1.y, bf);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int jg = 0; jg < 4; ++jg) {
-      if (2 * jg >= nkb) break;
-      const double* me = mbuf + ((2 * jg) * 32 + lane) * 4;
-      const double2 e0 = *reinterpret_cast<const double2*>(me), e1 = *reinterpret_cast<const double2*>(me + 2);
-      const double2 o0 = *reinterpret_cast<const double2*>(me + 128), o1 = *reinterpret_cast<const double2*>(me + 130);
-      const double av[8] = {e0.x, o0.x, e0.y, o0.y, e1.x, o1.x, e1.y, o1.y};
-#pragma unroll
-      for (int ib = 0; ib < 8; ++ib) {
-        const double* brow = bbuf + (size_t)(4 * ib + lk) * T;
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          const double bf = (8 * nb + lr < T) ? brow[8 * nb + lr] : 0.0;
-          dmma884(acc[jg][nb][0], acc[jg][nb][1], av[ib], bf);
-        }
-      }
-    }
-  }
-  store_outputs<T, FWD>(acc, a, row0, c0, w, h, uoff, lr, lk);
-}
-
 int pick_T(int t) { return t <= 1 ? 1 : t <= 2 ? 2 : t <= 4 ? 4 : t <= 8 ? 8 : t <= 16 ? 16 : 32; }
 
 int ensure_work(pcu_bj* bj, int T) {
@@ -842,30 +711,6 @@ void launch_one(int nu, cudaStream_t st, const SweepArgs& a) {
     configured = true;
   }
   launch_chain(sweep_kernel<T, FWD, D, NOALLOC, OCC, TCOPY>, nu, kThreads, bytes, st, a);
-}
-
-template <int T, bool FWD, int KMAX, int WARPS, bool TCOPY>
-void launch_tiny_one(int first, int count, cudaStream_t st, const SweepArgs& a) {
-  constexpr int bytes = WARPS * (KMAX * 32 + KMAX * T + 1) * (int)sizeof(double);   // + one mbarrier per warp
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(sweep_tiny_kernel<T, FWD, KMAX, WARPS, TCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    configured = true;
-  }
-  launch_chain(sweep_tiny_kernel<T, FWD, KMAX, WARPS, TCOPY>, (count + WARPS - 1) / WARPS, WARPS * 32, bytes, st, a, first, count);
-}
-
-// panels [first, first + count) are sorted by length, the last `nshort` ones have klen <= kTinyS: each class gets a
-// landing buffer of its own size (more resident warps for the shorter panels)
-template <int T, bool FWD>
-void launch_tiny(int first, int count, int nshort, cudaStream_t st, const SweepArgs& a, bool tcopy) {
-  const int nlong = count - nshort;
-  if (FWD || tcopy) {
-    if (nlong > 0) launch_tiny_one<T, FWD, kTinyK, 4, !FWD>(first, nlong, st, a);
-    if (nshort > 0) launch_tiny_one<T, FWD, kTinyS, 8, !FWD>(first + nlong, nshort, st, a);
-  } else {
-    launch_tiny_one<T, false, kTinyK, 4, false>(first, count, st, a);   // a tile-wise backward slice always lands a whole tile
-  }
 }
 
 template <int T, bool FWD>
@@ -947,38 +792,22 @@ int apply_T(pcu_bj* bj, const double* B, int ldb, double* X, int ldx, int t) {
     }
     const int nu = bj->fwd_unit_ptr[l + 1] - bj->fwd_unit_ptr[l];
     if (nu > 0) {
-      prof.mark("fwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->fwd_lvl_bytes[l] - bj->fwd_tiny_bytes[l]);
+      prof.mark("fwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->fwd_lvl_bytes[l]);
       a.units = bj->fwd_units + bj->fwd_unit_ptr[l];
       a.panels = bj->fwd_panels;
       a.data = bj->fwd_data;
       launch_sweep<T, true>(nu, st, a, false);
       PCU_LAUNCH_CHECK(c);
     }
-    if (bj->fwd_tinyn[l] > 0) {
-      prof.mark("fwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->fwd_tinyn[l]) + "/" + std::to_string(bj->fwd_tinys[l]), bj->fwd_tiny_bytes[l]);
-      a.panels = bj->fwd_panels;
-      a.data = bj->fwd_data;
-      launch_tiny<T, true>(bj->fwd_tiny0[l], bj->fwd_tinyn[l], bj->fwd_tinys[l], st, a, false);
-      c->launches++;
-      PCU_LAUNCH_CHECK(c);
-    }
   }
   for (int l = bj->nlevels - 1; l >= 0; --l) {
     const int nu = bj->bwd_unit_ptr[l + 1] - bj->bwd_unit_ptr[l];
     if (nu > 0) {
-      prof.mark("bwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->bwd_lvl_bytes[l] - bj->bwd_tiny_bytes[l]);
+      prof.mark("bwd L" + std::to_string(l) + " ctas=" + std::to_string(nu), bj->bwd_lvl_bytes[l]);
       a.units = bj->bwd_units + bj->bwd_unit_ptr[l];
       a.panels = bj->bwd_panels;
       a.data = bj->bwd_data ? bj->bwd_data : bj->fwd_data;
       launch_sweep<T, false>(nu, st, a, bj->bwd_data != nullptr);
-      PCU_LAUNCH_CHECK(c);
-    }
-    if (bj->bwd_tinyn[l] > 0) {
-      prof.mark("bwd L" + std::to_string(l) + " tiny=" + std::to_string(bj->bwd_tinyn[l]) + "/" + std::to_string(bj->bwd_tinys[l]), bj->bwd_tiny_bytes[l]);
-      a.panels = bj->bwd_panels;
-      a.data = bj->bwd_data ? bj->bwd_data : bj->fwd_data;
-      launch_tiny<T, false>(bj->bwd_tiny0[l], bj->bwd_tinyn[l], bj->bwd_tinys[l], st, a, bj->bwd_data != nullptr);
-      c->launches++;
       PCU_LAUNCH_CHECK(c);
     }
   }

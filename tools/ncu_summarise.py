@@ -69,7 +69,7 @@ if os.path.exists(tr):
     keys = list(du.keys())
     n = len(keys) // 3
     last = keys[-n:]
-    out = {"what": "DRAM traffic of ONE block-Jacobi apply (%d launches: assemble_kernel, sweep_kernel, sweep_tiny_kernel; Poisson 128^3, t=8, S=8, one B200)" % n,
+    out = {"what": "DRAM traffic of ONE block-Jacobi apply (%d launches: assemble_kernel, assemble_wide_kernel, sweep_kernel; Poisson 128^3, t=8, S=8, one B200)" % n,
            "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'sweep|assemble' python tools/profile_apply.py 128 1 1  (tools/ncu_capture.sh step 2)",
            "commit": commit, "launches": n,
            "dram_bytes_read": sum(rd[k] for k in last), "dram_bytes_write": sum(wr[k] for k in last),
