@@ -9,4 +9,4 @@ for v in 1 0; do
   timeout 300 python tools/variants.py 64 1 8 2>&1 | grep " levels "
 done
 unset PREALPS_BJ_NO_LEAF_DIRECT
-bash tools/r02_run17.sh
+bash tools/runs/r02_run17.sh
