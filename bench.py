@@ -342,7 +342,7 @@ def main():
     stored = capi.stat("bj_stored_bytes_t%d" % args.t)
     traffic, traffic_file, traffic_commit = ncu_traffic()
     roofline = {"bound": "hbm",
-                "kernel": "block-Jacobi apply = assemble_kernel + sweep_kernel + sweep_tiny_kernel<%d> over all levels of the forest, "
+                "kernel": "block-Jacobi apply = assemble_kernel + sweep_kernel<%d> over all levels of the forest, "
                           "forward + backward (the launch group of one pcu_bj_apply: ~86 %% of an iteration)" % args.t,
                 "achieved": bj["achieved_gbs"], "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
                 "frac": bj["achieved_gbs"] / peak, "traffic": traffic,
@@ -351,9 +351,14 @@ def main():
                 "algorithmic_bytes_per_apply": bj["algorithmic_bytes"],
                 "stored_bytes_per_apply": stored, "achieved_counting_stored_bytes": stored / (bj["ms"] * 1e-3) / 1e9,
                 "note": "algorithmic bytes (SURVEY.md 8d, dense-supernode form): 2 x (8 B x EXACT nnz(L) + 8 B x rows) + 4 x m x t x 8 B; "
-                        "stored bytes = what the sweeps move: both panel copies with the explicit zeros of the relaxed supernodes "
+                        "stored bytes = what the sweeps move: the panels once per sweep with the explicit zeros of the relaxed supernodes "
                         "and the 32-row panel padding, the work vectors and the update rows; median of 11 applies timed alone, "
                         "L2 flushed before each, CUDA events on the library stream"}
+    # SURVEY.md 8(d), whole solve: the algorithmic bytes of one iteration (block-Jacobi apply + SpMM + fused dense passes, per GPU)
+    # over the measured time of an iteration inside the timed region
+    it_bytes = sum(k["algorithmic_bytes"] for k in kern.values())
+    it_gbs = it_bytes / (ms_total / args.steps * 1e-3) / 1e9
+    roofline["whole_iteration"] = {"algorithmic_bytes": it_bytes, "achieved": it_gbs, "unit": "GB/s", "frac": it_gbs / peak}
 
     if rank == 0:
         cpu = None
