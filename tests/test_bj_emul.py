@@ -87,6 +87,37 @@ def test_factor_and_solve_match_direct_solver(emul, gen, N, nblk, ts, copies, pw
     lib.pcu_bj_destroy(bj)
 
 
+def test_update_matrices_share_their_workspace(emul):
+    """the (h-w)^2 update matrices of the multifrontal factorisation live from their supernode's level to their parent's only and
+    get first-fit offsets over that interval (bj_factor.cu): the workspace is smaller than the sum of all of them, and the
+    factor + solve still match a direct solver (an overlap of two live matrices would corrupt the factor)"""
+    lib, ctx = emul
+    lib.pcu_bj_stat.restype = C.c_double
+    A = gen_matrices.poisson7(11).tocsr()
+    n = A.shape[0]
+    rc, bj, cuts, blocks = factor(emul, A, 1)
+    assert rc == 0, lib.pcu_last_error()
+    ws = lib.pcu_bj_stat(bj, 10)
+    # all update matrices at once: recompute from the symbolic structure the library reports
+    N = n
+    U = sp.triu(A, format="csr"); U.sort_indices()
+    perm = np.zeros(N, np.int32); nsuper = C.c_int(); sn_col = np.zeros(N + 1, np.int32); sn_rowptr = np.zeros(N + 1, np.int64)
+    sn_rows = np.zeros(400 * N, np.int32); sn_parent = np.zeros(N, np.int32); sn_level = np.zeros(N, np.int32); st = np.zeros(4)
+    assert lib.pcu_bj_analyze(N, ip(U.indptr.astype(np.int32)), ip(U.indices.astype(np.int32)), 1, ip(perm), C.byref(nsuper), ip(sn_col),
+                              sn_rowptr.ctypes.data_as(C.POINTER(C.c_longlong)), ip(sn_rows), C.c_longlong(400 * N), ip(sn_parent),
+                              ip(sn_level), dp(st)) == 0
+    ns = nsuper.value
+    w = np.diff(sn_col[:ns + 1]).astype(np.int64); h = np.diff(sn_rowptr[:ns + 1]).astype(np.int64)
+    total = 8.0 * float(((h - w) ** 2).sum())
+    assert 0 < ws < 0.8 * total, (ws, total)
+    B = np.random.default_rng(0).standard_normal((n, 4))
+    X = np.full((n, 4), np.nan)
+    assert lib.pcu_bj_apply(bj, dp(B), 4, dp(X), 4, 4) == 0
+    ref = direct(blocks, cuts, B)
+    assert np.linalg.norm(X - ref) <= 1e-12 * np.linalg.norm(ref)
+    lib.pcu_bj_destroy(bj)
+
+
 def test_indefinite_block_is_rejected(emul):
     lib, ctx = emul
     A = gen_matrices.poisson7(4).tolil()
