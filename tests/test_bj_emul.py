@@ -118,6 +118,17 @@ def test_update_matrices_share_their_workspace(emul):
     lib.pcu_bj_destroy(bj)
 
 
+def test_panel_offsets_closed_form(tmp_path):
+    """bj.h: panel_cum(w, p), the doubles stored in front of slice p of a supernode (what lets the backward sweep find the forward
+    panels without an offset table), against the plain sum of the slice sizes for every width up to 700 and 60 slices"""
+    import subprocess
+    exe = str(tmp_path / "panel_cum_check")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "tests", "emul"), "-I" + os.path.join(ROOT, "prealps_b200", "csrc"),
+                    "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "emul", "panel_cum_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "panel_cum ok" in out.stdout, out.stdout
+
+
 def test_indefinite_block_is_rejected(emul):
     lib, ctx = emul
     A = gen_matrices.poisson7(4).tolil()
